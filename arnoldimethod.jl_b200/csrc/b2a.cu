@@ -1,0 +1,1372 @@
+// b2a.cu - engine and C ABI of libb200arnoldi.so (see include/b200arnoldi.h).
+//
+// One translation unit: the CUDA kernels (kernels_*.cuh), the host m x m algebra
+// (host_dense.hpp), the device engine that strings them into Arnoldi sweeps, the C++
+// restatement of the restart driver `_partialschur` (src/run.jl:224-392 of the reference)
+// and the extern "C" entry points.
+//
+// Execution model: a whole `iterate_arnoldi!(A, arnoldi, from:to)` sweep is enqueued on one
+// CUDA stream without any host round trip.  Every data-dependent decision of
+// src/expansion.jl (second Gram-Schmidt pass at :91, breakdown at :99) is taken on the
+// device from all-reduced scalars; the kernels of the conditional second pass gate
+// themselves, and a breakdown raises a `poison` flag that turns the rest of the sweep into
+// no-ops.  The host synchronises once per sweep, reads back the new H columns, and - only if
+// a breakdown happened - re-seeds that column (reinitialize!) and resumes the sweep.
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <chrono>
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "b200arnoldi.h"
+#include "device_common.cuh"
+#include "host_dense.hpp"
+#include "kernels_cgs.cuh"
+#include "kernels_rotate.cuh"
+#include "kernels_spmv.cuh"
+
+using b2a::cdouble;
+using b2a::host::cplx;
+
+// =============================================================================== errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      (void)cudaGetLastError();                                                            \
+      return fail(e__ == cudaErrorMemoryAllocation ? B2A_ERR_OOM : B2A_ERR_CUDA,           \
+                  std::string(#expr) + ": " + cudaGetErrorString(e__));                    \
+    }                                                                                      \
+  } while (0)
+#define B2A_TRY(expr)            \
+  do {                           \
+    int s__ = (expr);            \
+    if (s__ != B2A_OK) return s__; \
+  } while (0)
+#define ARG_CHECK(cond, msg) \
+  do {                       \
+    if (!(cond)) return fail(B2A_ERR_ARGUMENT, msg); \
+  } while (0)
+
+// ================================================================================ NCCL
+// NCCL is resolved at run time (dlopen) so that the library loads on hosts without it and
+// re-uses the libnccl.so.2 the host program (PyTorch) has already mapped.
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                            cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int load_nccl() {
+  if (g_nccl.handle) return B2A_OK;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  void *h = nullptr;
+  for (const char *nm : names) {
+    h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return fail(B2A_ERR_NCCL, std::string("dlopen(libnccl.so.2) failed: ") + dlerror());
+#define LOAD(sym)                                                                  \
+  g_nccl.sym = reinterpret_cast<decltype(g_nccl.sym)>(dlsym(h, "nccl" #sym));      \
+  if (!g_nccl.sym) return fail(B2A_ERR_NCCL, "dlsym(nccl" #sym ") failed")
+  LOAD(GetUniqueId);
+  LOAD(CommInitRank);
+  LOAD(CommDestroy);
+  LOAD(AllReduce);
+  LOAD(AllGather);
+  LOAD(Broadcast);
+  LOAD(GroupStart);
+  LOAD(GroupEnd);
+  LOAD(GetErrorString);
+#undef LOAD
+  g_nccl.handle = h;
+  return B2A_OK;
+}
+#define NCCL_TRY(expr)                                                                           \
+  do {                                                                                           \
+    ncclResult_t r__ = (expr);                                                                   \
+    if (r__ != ncclSuccess)                                                                      \
+      return fail(B2A_ERR_NCCL, std::string(#expr) + ": " + g_nccl.GetErrorString(r__));         \
+  } while (0)
+
+// ============================================================================== handles
+struct b2a_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+  int64_t launches = 0;
+  int num_sms = b2a::kSMs;
+  int *d_zero = nullptr;  // a device int that is always 0 (poison stand-in outside sweeps)
+};
+
+enum OpKind { OP_CSR = 0, OP_CSC_SCATTER = 1, OP_CALLBACK = 2 };
+
+struct b2a_op {
+  b2a_ctx *ctx = nullptr;
+  int dtype = B2A_F64;
+  int kind = OP_CSR;
+  int64_t n_local = 0, n_global = 0, row_offset = 0, nnz = 0;
+  int64_t *d_ptr = nullptr;  // rowptr (CSR) / colptr (CSC), 0-based
+  int32_t *d_idx = nullptr;  // colind (CSR) / rowind (CSC), 0-based, global
+  void *d_vals = nullptr;
+  bool owns = true;
+  int lpr = 8;  // lanes per row (column)
+  b2a_matvec_fn fn = nullptr;
+  void *user = nullptr;
+};
+
+struct b2a_ws {
+  b2a_ctx *ctx = nullptr;
+  int dtype = B2A_F64;
+  int64_t n_local = 0, n_global = 0, row_offset = 0, ld = 0;
+  int maxdim = 0;
+  size_t esz = 8;
+  void *dV = nullptr;  // ld x (maxdim+1)
+  std::vector<char> H, Q;  // host, column-major: (maxdim+1) x maxdim and maxdim x maxdim
+  // device scratch
+  void *dH = nullptr;        // (maxdim+1) x maxdim, filled column by column by cgs_finish
+  int *dinfo = nullptr;      // per column: bit0 = second pass, bit1 = breakdown
+  char *hb1 = nullptr;       // [h1 (j T) | rsq]
+  char *hb2 = nullptr;       // [h2 (j T) | w1sq]
+  double *w2sq = nullptr;
+  void *partials = nullptr;  // T x (maxdim+2) x dots_grid
+  double *partials2 = nullptr;
+  b2a::SweepState *state = nullptr;
+  void *dQ = nullptr;     // maxdim x maxdim
+  void *xfull = nullptr;  // n_global (multi-GPU operator input)
+  char *pinned = nullptr;  // host staging for read-backs
+  size_t pinned_bytes = 0;
+  int dots_grid_max = 0, upd_grid_max = 0;
+  uint64_t reseed_counter = 0;
+  std::vector<int64_t> all_offsets, all_counts;  // row partition over ranks
+  bool uniform_partition = true;
+};
+
+template <class HT> struct Dev;
+template <> struct Dev<double> { using type = double; };
+template <> struct Dev<cplx> { using type = cdouble; };
+
+static inline size_t dtype_size(int dtype) { return dtype == B2A_C64 ? 16 : 8; }
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ======================================================================= device engine
+namespace eng {
+
+template <class DT> static inline DT *col(b2a_ws *ws, int c0) {
+  return reinterpret_cast<DT *>(ws->dV) + (int64_t)c0 * ws->ld;
+}
+
+static int allreduce_f64(b2a_ctx *ctx, void *buf, size_t count) {
+  if (ctx->world == 1) return B2A_OK;
+  NCCL_TRY(g_nccl.AllReduce(buf, buf, count, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
+  return B2A_OK;
+}
+
+// ---- Gram-Schmidt launches ------------------------------------------------------
+template <class DT, int CPW, int U>
+static int launch_dots_inst(b2a_ws *ws, const DT *V, const DT *v, int ncols, DT *hout, double *nrm2,
+                            const double *g_rsq, const double *g_w1sq) {
+  constexpr int PV = b2a::Scalar<DT>::per_vec;
+  const int64_t n = ws->n_local;
+  const int64_t quantum = 32 * PV * U;
+  int64_t grid = std::max<int64_t>(1, std::min<int64_t>(ws->dots_grid_max, cdiv(n, quantum)));
+  const int64_t rows_per_cta = round_up(cdiv(n, grid), quantum);
+  grid = std::max<int64_t>(1, cdiv(n, rows_per_cta));
+  b2a::cgs_dots_kernel<DT, CPW, U><<<(unsigned)grid, b2a::kCgsThreads, 0, ws->ctx->stream>>>(
+      V, ws->ld, v, n, ncols, rows_per_cta, reinterpret_cast<DT *>(ws->partials), hout, nrm2,
+      &ws->state->ticket[0], &ws->state->poison, g_rsq, g_w1sq);
+  ws->ctx->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return B2A_OK;
+}
+
+// dots over panel columns [0, ncols) in blocks of at most 64 columns
+template <class DT>
+static int launch_dots(b2a_ws *ws, int ncols, const DT *v, DT *hout, double *nrm2, const double *g_rsq,
+                       const double *g_w1sq) {
+  const DT *V = col<DT>(ws, 0);
+  int done = 0;
+  bool first = true;
+  do {
+    const int nc = std::min(64, ncols - done);
+    const int cpw = std::max(1, (nc + b2a::kCgsWarps - 1) / b2a::kCgsWarps);
+    double *nrm = first ? nrm2 : nullptr;
+    const DT *Vb = V + (int64_t)done * ws->ld;
+    DT *hb = hout + done;
+    int s;
+    switch (cpw) {
+      case 1: s = launch_dots_inst<DT, 1, 8>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq); break;
+      case 2: s = launch_dots_inst<DT, 2, 8>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq); break;
+      case 3: s = launch_dots_inst<DT, 3, 4>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq); break;
+      case 4: s = launch_dots_inst<DT, 4, 4>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq); break;
+      case 5: s = launch_dots_inst<DT, 5, 2>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq); break;
+      case 6: s = launch_dots_inst<DT, 6, 2>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq); break;
+      case 7: s = launch_dots_inst<DT, 7, 2>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq); break;
+      default: s = launch_dots_inst<DT, 8, 2>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq); break;
+    }
+    B2A_TRY(s);
+    done += nc;
+    first = false;
+  } while (done < ncols);
+  return B2A_OK;
+}
+
+template <class DT>
+static int launch_update(b2a_ws *ws, int ncols, DT *v, const DT *h, double *nrm2, const double *g_rsq,
+                         const double *g_w1sq) {
+  constexpr int PV = b2a::Scalar<DT>::per_vec;
+  const int64_t nvec = cdiv(ws->n_local, PV);
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(ws->upd_grid_max, cdiv(nvec, b2a::kCgsThreads)));
+  b2a::cgs_update_kernel<DT><<<(unsigned)grid, b2a::kCgsThreads, ncols * sizeof(DT), ws->ctx->stream>>>(
+      col<DT>(ws, 0), ws->ld, v, ws->n_local, ncols, h, ws->partials2, nrm2, &ws->state->ticket[1],
+      &ws->state->poison, g_rsq, g_w1sq);
+  ws->ctx->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return B2A_OK;
+}
+
+// One orthogonalisation of column index j (0-based; panel = columns 0..j-1).
+// mode: 0 Arnoldi step, 1 re-seed, 2 normalise only (j == 0).
+template <class DT> static int enqueue_cgs(b2a_ws *ws, int j, int mode, int step) {
+  b2a_ctx *ctx = ws->ctx;
+  DT *v = col<DT>(ws, j);
+  DT *h1 = reinterpret_cast<DT *>(ws->hb1);
+  DT *h2 = reinterpret_cast<DT *>(ws->hb2);
+  double *rsq = reinterpret_cast<double *>(h1 + j);
+  double *w1sq = reinterpret_cast<double *>(h2 + j);
+  const size_t hd = (size_t)j * sizeof(DT) / sizeof(double);  // doubles in a j-vector of DT
+
+  if (j == 0 || mode == 2) {
+    B2A_TRY(launch_dots<DT>(ws, 0, v, h1, rsq, nullptr, nullptr));
+    B2A_TRY(allreduce_f64(ctx, rsq, 1));
+    mode = 2;
+  } else {
+    // pass 1: h = V' v, rnorm^2 ; v -= V h, wnorm^2          (expansion.jl:81-88)
+    B2A_TRY(launch_dots<DT>(ws, j, v, h1, rsq, nullptr, nullptr));
+    B2A_TRY(allreduce_f64(ctx, h1, hd + 1));
+    B2A_TRY(launch_update<DT>(ws, j, v, h1, w1sq, nullptr, nullptr));
+    B2A_TRY(allreduce_f64(ctx, w1sq, 1));
+    // pass 2, gated on the device by wnorm < eta * rnorm      (expansion.jl:91-96)
+    B2A_TRY(launch_dots<DT>(ws, j, v, h2, nullptr, rsq, w1sq));
+    B2A_TRY(allreduce_f64(ctx, h2, hd));
+    B2A_TRY(launch_update<DT>(ws, j, v, h2, ws->w2sq, rsq, w1sq));
+    B2A_TRY(allreduce_f64(ctx, ws->w2sq, 1));
+  }
+  constexpr int PV = b2a::Scalar<DT>::per_vec;
+  const int64_t nvec = cdiv(ws->n_local, PV);
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(ws->upd_grid_max, cdiv(nvec, 256)));
+  DT *Hcol = reinterpret_cast<DT *>(ws->dH) + (int64_t)(std::max(j, 1) - 1) * (ws->maxdim + 1);
+  b2a::cgs_finish_kernel<DT><<<(unsigned)grid, 256, 0, ctx->stream>>>(
+      v, ws->n_local, j, h1, h2, rsq, w1sq, ws->w2sq, Hcol, ws->dinfo + j, ws->state, step, mode);
+  ctx->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return B2A_OK;
+}
+
+// ---- operator -------------------------------------------------------------------
+template <class DT, int LPR>
+static void launch_spmv_vec(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms) {
+  constexpr int U = 4;
+  const int64_t threads = cdiv(A->n_local, U) * LPR;
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * 8, cdiv(threads, 256)));
+  b2a::spmv_csr_vector_kernel<DT, LPR, U><<<(unsigned)grid, 256, 0, st>>>(
+      A->n_local, A->d_ptr, A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y, poison);
+}
+
+template <class DT, int LPC>
+static void launch_spmv_csc(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms) {
+  const int64_t threads = A->n_global * LPC;
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * 8, cdiv(threads, 256)));
+  b2a::spmv_csc_scatter_kernel<DT, LPC><<<(unsigned)grid, 256, 0, st>>>(
+      A->n_global, A->d_ptr, A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y, poison);
+}
+
+// y = A x for the local rows; x_local / y are workspace columns.
+template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, int jdst0) {
+  b2a_ctx *ctx = ws->ctx;
+  const DT *xl = col<DT>(ws, jsrc0);
+  DT *y = col<DT>(ws, jdst0);
+  const int *poison = &ws->state->poison;
+  if (A->kind == OP_CALLBACK) {
+    const int rc = A->fn(A->user, xl, y, ws->n_local, ctx->stream);
+    if (rc != 0) return fail(B2A_ERR_CALLBACK, "matvec callback returned " + std::to_string(rc));
+    return B2A_OK;
+  }
+  const DT *x = xl;
+  if (ctx->world > 1) {
+    // x-exchange: every shard needs (in general) all of x.  Uniform partitions use one
+    // all-gather; ragged ones a group of broadcasts.
+    DT *xf = reinterpret_cast<DT *>(ws->xfull);
+    const size_t dpe = sizeof(DT) / sizeof(double);
+    if (ws->uniform_partition) {
+      NCCL_TRY(g_nccl.AllGather(xl, xf, (size_t)ws->all_counts[0] * dpe, ncclFloat64, ctx->comm, ctx->stream));
+    } else {
+      NCCL_TRY(g_nccl.GroupStart());
+      for (int r = 0; r < ctx->world; ++r)
+        NCCL_TRY(g_nccl.Broadcast(xl, xf + ws->all_offsets[r], (size_t)ws->all_counts[r] * dpe, ncclFloat64, r,
+                                  ctx->comm, ctx->stream));
+      NCCL_TRY(g_nccl.GroupEnd());
+    }
+    x = xf;
+  }
+  if (A->kind == OP_CSC_SCATTER) {
+    b2a::zero_vector_kernel<DT><<<(unsigned)std::min<int64_t>(ctx->num_sms * 8, std::max<int64_t>(1, cdiv(A->n_local, 256))), 256, 0, ctx->stream>>>(y, A->n_local, poison);
+    ctx->launches++;
+    switch (A->lpr) {
+      case 1:
+      case 2: launch_spmv_csc<DT, 2>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
+      case 4: launch_spmv_csc<DT, 4>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
+      case 8: launch_spmv_csc<DT, 8>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
+      case 16: launch_spmv_csc<DT, 16>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
+      default: launch_spmv_csc<DT, 32>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
+    }
+  } else {
+    switch (A->lpr) {
+      case 1: {
+        const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, cdiv(A->n_local, 256)));
+        b2a::spmv_csr_scalar_kernel<DT><<<(unsigned)grid, 256, 0, ctx->stream>>>(
+            A->n_local, A->d_ptr, A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y, poison);
+        break;
+      }
+      case 2: launch_spmv_vec<DT, 2>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
+      case 4: launch_spmv_vec<DT, 4>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
+      case 8: launch_spmv_vec<DT, 8>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
+      case 16: launch_spmv_vec<DT, 16>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
+      default: launch_spmv_vec<DT, 32>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
+    }
+  }
+  ctx->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return B2A_OK;
+}
+
+// ---- basis rotation ---------------------------------------------------------------
+template <class DT, int R>
+static bool try_rotate(b2a_ws *ws, int col0, int K, int N, int move_src, int move_dst) {
+  const int Npad = (N + 3) & ~3;
+  const size_t smem = ((size_t)(K + 1) * R + (size_t)K * Npad) * sizeof(DT);
+  if (smem > 200 * 1024) return false;
+  auto kern = b2a::rotate_basis_kernel<DT, R>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  const int64_t grid = std::max<int64_t>(1, cdiv(ws->n_local, R));
+  kern<<<(unsigned)grid, 256, smem, ws->ctx->stream>>>(reinterpret_cast<DT *>(ws->dV), ws->ld, ws->n_local, col0, K,
+                                                         N, reinterpret_cast<const DT *>(ws->dQ), move_src, move_dst);
+  ws->ctx->launches++;
+  return true;
+}
+
+// V[:, col0 : col0+N) <- V[:, col0 : col0+K) * Qp  (Qp = K x N packed, host), optional column move
+template <class HT>
+static int rotate(b2a_ws *ws, int col0, int K, int N, const HT *Qp, int move_src, int move_dst) {
+  using DT = typename Dev<HT>::type;
+  if (N <= 0 || K <= 0) return B2A_OK;
+  if (move_src == move_dst) move_src = move_dst = -1;
+  CUDA_TRY(cudaMemcpyAsync(ws->dQ, Qp, (size_t)K * N * sizeof(HT), cudaMemcpyHostToDevice, ws->ctx->stream));
+  bool ok = try_rotate<DT, 128>(ws, col0, K, N, move_src, move_dst);
+  if (!ok) ok = try_rotate<DT, 64>(ws, col0, K, N, move_src, move_dst);
+  if (!ok) ok = try_rotate<DT, 32>(ws, col0, K, N, move_src, move_dst);
+  if (!ok) return fail(B2A_ERR_ARGUMENT, "basis rotation: Krylov dimension too large for one shared-memory tile");
+  CUDA_TRY(cudaGetLastError());
+  // Qp is a host temporary of the caller: make sure the copy has been consumed
+  CUDA_TRY(cudaStreamSynchronize(ws->ctx->stream));
+  return B2A_OK;
+}
+
+static double cgs_pass_bytes(const b2a_ws *ws, int j) {
+  return (2.0 * j + 3.0) * (double)ws->n_local * (double)ws->esz;  // B_cgs(j)
+}
+static double scal_bytes(const b2a_ws *ws) { return 2.0 * (double)ws->n_local * (double)ws->esz; }
+
+static double op_bytes(const b2a_op *A) {
+  if (A->kind == OP_CALLBACK) return 0.0;
+  const double s = (double)dtype_size(A->dtype);
+  const double nptr = (A->kind == OP_CSC_SCATTER ? A->n_global : A->n_local) + 1.0;
+  return (double)A->nnz * (s + 4.0) + 8.0 * nptr + 2.0 * (double)A->n_local * s;
+}
+
+static uint64_t reseed_key(uint64_t seed, uint64_t counter) {
+  return b2a::splitmix64(seed ^ (0x632BE59BD9B4E019ull * (counter + 1)));
+}
+
+template <class DT> static int enqueue_fill(b2a_ws *ws, int j0, uint64_t key) {
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)ws->ctx->num_sms * 8, cdiv(ws->n_local, 256)));
+  b2a::fill_uniform_kernel<DT><<<(unsigned)grid, 256, 0, ws->ctx->stream>>>(col<DT>(ws, j0), ws->n_local,
+                                                                            ws->row_offset, key, ws->ctx->d_zero);
+  ws->ctx->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return B2A_OK;
+}
+
+struct Readback {
+  int poison;
+  unsigned long long second_passes;
+};
+
+// reinitialize!(arnoldi, j, populate!) for 0-based target column j.
+template <class HT> static int reinitialize(b2a_ws *ws, int j, int mode, uint64_t seed, int *ok, b2a_stats *st) {
+  using DT = typename Dev<HT>::type;
+  b2a_ctx *ctx = ws->ctx;
+  const int64_t l0 = ctx->launches;
+  if (mode == B2A_INIT_RAND) B2A_TRY(enqueue_fill<DT>(ws, j, reseed_key(seed, ws->reseed_counter++)));
+  B2A_TRY(enqueue_cgs<DT>(ws, j, j == 0 ? 2 : 1, 0));
+  int info = 0;
+  CUDA_TRY(cudaMemcpyAsync(ws->pinned, ws->dinfo + j, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  std::memcpy(&info, ws->pinned, sizeof(int));
+  if (ok) *ok = (j == 0) ? 1 : ((info & 2) ? 0 : 1);
+  if (st) {
+    const int passes = (j == 0) ? 0 : ((info & 1) ? 2 : 1);
+    st->passes += passes;
+    st->bytes += passes * cgs_pass_bytes(ws, j) + scal_bytes(ws);
+    st->launches += ctx->launches - l0;
+  }
+  return B2A_OK;
+}
+
+// iterate_arnoldi!(A, arnoldi, from:to) - 1-based steps as in the reference.
+template <class HT>
+static int iterate_arnoldi(b2a_ws *ws, b2a_op *A, int from, int to, uint64_t seed, b2a_stats *st) {
+  using DT = typename Dev<HT>::type;
+  b2a_ctx *ctx = ws->ctx;
+  const int m1 = ws->maxdim + 1;
+  HT *H = reinterpret_cast<HT *>(ws->H.data());
+  int j = from;
+  while (j <= to) {
+    const int64_t l0 = ctx->launches;
+    for (int s = j; s <= to; ++s) {
+      B2A_TRY(enqueue_matvec<DT>(ws, A, s - 1, s));  // V[:, s+1] = A V[:, s]   (expansion.jl:121)
+      B2A_TRY(enqueue_cgs<DT>(ws, s, 0, s));         // orthogonalize!(arnoldi, s)  (expansion.jl:127)
+    }
+    // one read-back per sweep: new H columns, per-column info, sweep state
+    const int ncols = to - j + 1;
+    char *p = ws->pinned;
+    const size_t hbytes = (size_t)ncols * m1 * sizeof(HT);
+    CUDA_TRY(cudaMemcpyAsync(p, reinterpret_cast<char *>(ws->dH) + (size_t)(j - 1) * m1 * sizeof(HT), hbytes,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(p + hbytes, ws->dinfo + j, ncols * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(p + hbytes + ncols * sizeof(int), ws->state, sizeof(b2a::SweepState),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    b2a::SweepState state;
+    std::memcpy(&state, p + hbytes + ncols * sizeof(int), sizeof(state));
+    const int *info = reinterpret_cast<const int *>(p + hbytes);
+    const int last = state.poison ? state.poison : to;  // last step that really executed
+    const HT *Hn = reinterpret_cast<const HT *>(p);
+    for (int s = j; s <= last; ++s) {
+      for (int i = 0; i <= s; ++i) H[(size_t)(s - 1) * m1 + i] = Hn[(size_t)(s - j) * m1 + i];
+      if (st) {
+        const int passes = (info[s - j] & 1) ? 2 : 1;
+        st->matvecs += 1;
+        st->passes += passes;
+        st->second_passes += (info[s - j] & 1);
+        st->bytes += op_bytes(A) + passes * cgs_pass_bytes(ws, s) + ((info[s - j] & 2) ? 0.0 : scal_bytes(ws));
+      }
+    }
+    if (st) st->launches += ctx->launches - l0;
+    if (!state.poison) break;
+    // breakdown at step `last`: H[last+1, last] = 0 already; re-seed unless j == size(V,1)
+    if (st) st->breakdowns += 1;
+    CUDA_TRY(cudaMemsetAsync(&ws->state->poison, 0, sizeof(int), ctx->stream));
+    if ((int64_t)last != ws->n_global) {
+      int ok_unused;
+      B2A_TRY((reinitialize<HT>(ws, last, B2A_INIT_RAND, seed, &ok_unused, st)));  // expansion.jl:128
+    }
+    j = last + 1;
+  }
+  return B2A_OK;
+}
+
+}  // namespace eng
+
+// ================================================================= restart driver (host)
+namespace drv {
+
+using namespace b2a::host;
+
+template <class HT>
+static int rotate_basis(b2a_ws *ws, int purge, int k, int maxdim, const HT *Q, int ldq, b2a_stats *st) {
+  const int K = maxdim - purge + 1, N = k - purge + 1;
+  if (N <= 0) return B2A_OK;
+  std::vector<HT> Qp((size_t)K * N);
+  for (int o = 0; o < N; ++o)
+    for (int c = 0; c < K; ++c) Qp[(size_t)o * K + c] = Q[(size_t)(purge - 1 + o) * ldq + (purge - 1 + c)];
+  const int64_t l0 = ws->ctx->launches;
+  B2A_TRY((eng::rotate<HT>(ws, purge - 1, K, N, Qp.data(), maxdim, k)));
+  if (st) {
+    st->launches += ws->ctx->launches - l0;
+    st->bytes += (double)ws->n_local * ws->esz * (K + N + 2.0);  // B_rot
+  }
+  return B2A_OK;
+}
+
+template <class HT> static int rotate_final(b2a_ws *ws, int nconv, const HT *Q, int ldq, b2a_stats *st) {
+  if (nconv <= 0) return B2A_OK;
+  std::vector<HT> Qp((size_t)nconv * nconv);
+  for (int o = 0; o < nconv; ++o)
+    for (int c = 0; c < nconv; ++c) Qp[(size_t)o * nconv + c] = Q[(size_t)o * ldq + c];
+  const int64_t l0 = ws->ctx->launches;
+  B2A_TRY((eng::rotate<HT>(ws, 0, nconv, nconv, Qp.data(), -1, -1)));
+  if (st) {
+    st->launches += ws->ctx->launches - l0;
+    st->bytes += (double)ws->n_local * ws->esz * (2.0 * nconv);
+  }
+  return B2A_OK;
+}
+
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// _partialschur (src/run.jl:224-392)
+template <class HT>
+static int partialschur(b2a_ws *ws, b2a_op *A, int mindim, int maxdim, int nev, double tol, int restarts,
+                        int which, int active, uint64_t seed, b2a_history *hist, double *eig_out) {
+  const int m1 = ws->maxdim + 1;  // leading dimension of the workspace H
+  Mat<HT> H{reinterpret_cast<HT *>(ws->H.data()), maxdim + 1, maxdim, m1};
+  Mat<HT> Q{reinterpret_cast<HT *>(ws->Q.data()), maxdim, maxdim, ws->maxdim};
+  RestartScratch<HT> S(maxdim);
+  Ordering ordering{which};
+  b2a_stats *st = &hist->stats;
+
+  int k = mindim;
+  int64_t prods = std::max(0, mindim - active + 1);  // run.jl:264
+  double t0 = now_ms();
+  B2A_TRY((eng::iterate_arnoldi<HT>(ws, A, active, mindim, seed, st)));  // run.jl:267
+  hist->ms_expand += now_ms() - t0;
+
+  int iters = 0;
+  for (int iter = 1; iter <= restarts; ++iter) {
+    t0 = now_ms();
+    B2A_TRY((eng::iterate_arnoldi<HT>(ws, A, k + 1, maxdim, seed, st)));  // run.jl:272
+    prods += std::max(0, maxdim - k);                                        // run.jl:275
+    double t1 = now_ms();
+    hist->ms_expand += t1 - t0;
+
+    RestartPlan plan;
+    try {
+      plan = restart_decision(H, Q, maxdim, mindim, nev, tol, ordering, active, S);  // run.jl:278-360
+    } catch (const QRNoConvergence &e) {
+      return fail(B2A_ERR_QR, e.what());
+    }
+    double t2 = now_ms();
+    hist->ms_small += t2 - t1;
+
+    k = plan.k;
+    B2A_TRY((rotate_basis<HT>(ws, plan.purge, k, maxdim, Q.p, Q.ld, st)));  // run.jl:363-365
+    hist->ms_rotate += now_ms() - t2;
+
+    ++iters;
+    active = plan.nlock + 1;  // run.jl:368
+    if (active > nev) break;  // run.jl:370
+  }
+
+  const int nconverged = active - 1;
+  t0 = now_ms();
+  for (int j = 1; j <= maxdim; ++j)
+    for (int i = 1; i <= maxdim; ++i) Q(i, j) = (i == j) ? HT(1) : HT(0);
+  sortschur(H, Q, nconverged, ordering);  // run.jl:379
+  double t1 = now_ms();
+  hist->ms_small += t1 - t0;
+  B2A_TRY((rotate_final<HT>(ws, nconverged, Q.p, Q.ld, st)));  // run.jl:382-383
+  hist->ms_rotate += now_ms() - t1;
+
+  if (eig_out) {
+    std::vector<cplx> lams(maxdim);
+    copy_eigenvalues(lams.data(), H, 1, nconverged);  // run.jl:386
+    for (int i = 0; i < nconverged; ++i) {
+      eig_out[2 * i] = lams[i].real();
+      eig_out[2 * i + 1] = lams[i].imag();
+    }
+  }
+  hist->mvproducts = prods;
+  hist->nconverged = nconverged;
+  hist->converged = nconverged >= nev;
+  hist->nev = nev;
+  hist->restarts = iters;
+  return B2A_OK;
+}
+
+}  // namespace drv
+
+// ================================================================================= ABI
+extern "C" {
+
+int b2a_version(void) { return B2A_VERSION; }
+const char *b2a_last_error(void) { return g_err.c_str(); }
+
+static int ctx_common(int device, b2a_ctx *c) {
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(B2A_ERR_ARGUMENT, "no such CUDA device");
+  CUDA_TRY(cudaSetDevice(device));
+  c->device = device;
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(B2A_ERR_CUDA, std::string("libb200arnoldi is built for sm_100a only; device is ") + prop.name);
+  c->num_sms = prop.multiProcessorCount;
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaMalloc(&c->d_zero, sizeof(int)));
+  CUDA_TRY(cudaMemset(c->d_zero, 0, sizeof(int)));
+  return B2A_OK;
+}
+
+int b2a_ctx_create(int device, b2a_ctx **out) {
+  if (!out) return fail(B2A_ERR_ARGUMENT, "out is NULL");
+  b2a_ctx *c = new b2a_ctx();
+  int s = ctx_common(device, c);
+  if (s != B2A_OK) {
+    delete c;
+    return s;
+  }
+  *out = c;
+  return B2A_OK;
+}
+
+int b2a_nccl_unique_id(void *out128) {
+  B2A_TRY(load_nccl());
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  NCCL_TRY(g_nccl.GetUniqueId(&id));
+  std::memcpy(out128, &id, sizeof(id));
+  return B2A_OK;
+}
+
+int b2a_ctx_create_dist(int device, int rank, int world, const void *nccl_unique_id, b2a_ctx **out) {
+  if (!out) return fail(B2A_ERR_ARGUMENT, "out is NULL");
+  if (world < 1 || rank < 0 || rank >= world) return fail(B2A_ERR_ARGUMENT, "bad rank / world");
+  b2a_ctx *c = new b2a_ctx();
+  int s = ctx_common(device, c);
+  if (s != B2A_OK) {
+    delete c;
+    return s;
+  }
+  c->rank = rank;
+  c->world = world;
+  if (world > 1) {
+    s = load_nccl();
+    if (s != B2A_OK) {
+      delete c;
+      return s;
+    }
+    ncclUniqueId id;
+    std::memcpy(&id, nccl_unique_id, sizeof(id));
+    ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, id, rank);
+    if (r != ncclSuccess) {
+      delete c;
+      return fail(B2A_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+    }
+  }
+  *out = c;
+  return B2A_OK;
+}
+
+int b2a_ctx_destroy(b2a_ctx *ctx) {
+  if (!ctx) return B2A_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
+  if (ctx->d_zero) cudaFree(ctx->d_zero);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return B2A_OK;
+}
+
+int b2a_ctx_stream(b2a_ctx *ctx, void **stream) {
+  if (!ctx || !stream) return fail(B2A_ERR_ARGUMENT, "NULL argument");
+  *stream = ctx->stream;
+  return B2A_OK;
+}
+int b2a_ctx_sync(b2a_ctx *ctx) {
+  if (!ctx) return fail(B2A_ERR_ARGUMENT, "NULL ctx");
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return B2A_OK;
+}
+int b2a_ctx_rank(b2a_ctx *ctx, int *rank, int *world) {
+  if (!ctx) return fail(B2A_ERR_ARGUMENT, "NULL ctx");
+  if (rank) *rank = ctx->rank;
+  if (world) *world = ctx->world;
+  return B2A_OK;
+}
+int b2a_ctx_launch_count(b2a_ctx *ctx, int64_t *launches) {
+  if (!ctx || !launches) return fail(B2A_ERR_ARGUMENT, "NULL argument");
+  *launches = ctx->launches;
+  return B2A_OK;
+}
+
+// ------------------------------------------------------------------------- operators
+extern "C++" {
+template <class Src>
+__global__ void convert_index_kernel(const Src *__restrict__ src, int64_t count, int64_t base, int64_t *dst64,
+                                     int32_t *dst32) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const int64_t v = (int64_t)src[i] - base;
+    if (dst64) dst64[i] = v;
+    if (dst32) dst32[i] = (int32_t)v;
+  }
+}
+
+}  // extern "C++"
+
+// upload a host index array (32/64 bit, base 0/1) to a device int64 or int32 array
+static int upload_index(b2a_ctx *ctx, const void *host, int64_t count, int idx_width, int idx_base, int64_t *d64,
+                        int32_t *d32) {
+  if (count == 0) return B2A_OK;
+  if (idx_width == 32 && idx_base == 0 && d32) {
+    CUDA_TRY(cudaMemcpyAsync(d32, host, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+    return B2A_OK;
+  }
+  if (idx_width == 64 && idx_base == 0 && d64) {
+    CUDA_TRY(cudaMemcpyAsync(d64, host, count * 8, cudaMemcpyHostToDevice, ctx->stream));
+    return B2A_OK;
+  }
+  void *tmp = nullptr;
+  const size_t bytes = (size_t)count * (idx_width / 8);
+  CUDA_TRY(cudaMalloc(&tmp, bytes));
+  cudaError_t e = cudaMemcpyAsync(tmp, host, bytes, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    const unsigned grid = (unsigned)std::min<int64_t>(ctx->num_sms * 8, std::max<int64_t>(1, cdiv(count, 256)));
+    if (idx_width == 32)
+      convert_index_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>((const int32_t *)tmp, count, idx_base, d64, d32);
+    else
+      convert_index_kernel<int64_t><<<grid, 256, 0, ctx->stream>>>((const int64_t *)tmp, count, idx_base, d64, d32);
+    ctx->launches++;
+    e = cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(tmp);
+  CUDA_TRY(e);
+  return B2A_OK;
+}
+
+static int pick_lanes(int64_t nnz, int64_t nrows) {
+  const double avg = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
+  if (avg <= 1.5) return 1;
+  if (avg <= 3.0) return 2;
+  if (avg <= 6.0) return 4;
+  if (avg <= 12.0) return 8;
+  if (avg <= 24.0) return 16;
+  return 32;
+}
+
+static int op_alloc(b2a_ctx *ctx, b2a_op *op, int64_t nptr) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  CUDA_TRY(cudaMalloc(&op->d_ptr, (size_t)(nptr + 1) * 8));
+  CUDA_TRY(cudaMalloc(&op->d_idx, (size_t)std::max<int64_t>(op->nnz, 1) * 4));
+  CUDA_TRY(cudaMalloc(&op->d_vals, (size_t)std::max<int64_t>(op->nnz, 1) * dtype_size(op->dtype)));
+  return B2A_OK;
+}
+
+int b2a_op_destroy(b2a_op *op) {
+  if (!op) return B2A_OK;
+  if (op->owns) {
+    cudaSetDevice(op->ctx->device);
+    if (op->d_ptr) cudaFree(op->d_ptr);
+    if (op->d_idx) cudaFree(op->d_idx);
+    if (op->d_vals) cudaFree(op->d_vals);
+  }
+  delete op;
+  return B2A_OK;
+}
+
+static int check_op_args(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_global, int64_t row_offset,
+                         int64_t nnz, int idx_width, int idx_base) {
+  if (!ctx) return fail(B2A_ERR_ARGUMENT, "NULL ctx");
+  ARG_CHECK(dtype == B2A_F64 || dtype == B2A_C64, "dtype must be B2A_F64 or B2A_C64");
+  ARG_CHECK(n_local >= 0 && n_global >= 1 && row_offset >= 0 && nnz >= 0, "negative size");
+  if (row_offset + n_local > n_global)
+    return fail(B2A_ERR_DIMENSION, "row block exceeds the matrix order (matrix must be square n_global x n_global)");
+  ARG_CHECK(n_global < (int64_t)2147483647, "matrix order must fit 32-bit column indices");
+  ARG_CHECK(idx_width == 32 || idx_width == 64, "idx_width must be 32 or 64");
+  ARG_CHECK(idx_base == 0 || idx_base == 1, "idx_base must be 0 or 1");
+  return B2A_OK;
+}
+
+int b2a_csr_create(b2a_ctx *ctx, int dtype, int64_t n_rows_local, int64_t n_global, int64_t row_offset, int64_t nnz,
+                   const void *rowptr, const void *colind, const void *vals, int idx_width, int idx_base,
+                   b2a_op **out) {
+  B2A_TRY(check_op_args(ctx, dtype, n_rows_local, n_global, row_offset, nnz, idx_width, idx_base));
+  if (!rowptr || (nnz > 0 && (!colind || !vals)) || !out) return fail(B2A_ERR_ARGUMENT, "NULL array");
+  b2a_op *op = new b2a_op();
+  op->ctx = ctx;
+  op->dtype = dtype;
+  op->kind = OP_CSR;
+  op->n_local = n_rows_local;
+  op->n_global = n_global;
+  op->row_offset = row_offset;
+  op->nnz = nnz;
+  op->lpr = pick_lanes(nnz, n_rows_local);
+  int s = op_alloc(ctx, op, n_rows_local);
+  if (s == B2A_OK) s = upload_index(ctx, rowptr, n_rows_local + 1, idx_width, idx_base, op->d_ptr, nullptr);
+  if (s == B2A_OK) s = upload_index(ctx, colind, nnz, idx_width, idx_base, nullptr, op->d_idx);
+  if (s == B2A_OK && nnz > 0) {
+    cudaError_t e = cudaMemcpyAsync(op->d_vals, vals, (size_t)nnz * dtype_size(dtype), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) s = fail(B2A_ERR_CUDA, cudaGetErrorString(e));
+  }
+  if (s != B2A_OK) {
+    b2a_op_destroy(op);
+    return s;
+  }
+  *out = op;
+  return B2A_OK;
+}
+
+int b2a_csr_create_device(b2a_ctx *ctx, int dtype, int64_t n_rows_local, int64_t n_global, int64_t row_offset,
+                          int64_t nnz, const int64_t *d_rowptr, const int32_t *d_colind, const void *d_vals,
+                          b2a_op **out) {
+  B2A_TRY(check_op_args(ctx, dtype, n_rows_local, n_global, row_offset, nnz, 32, 0));
+  if (!d_rowptr || !out) return fail(B2A_ERR_ARGUMENT, "NULL array");
+  b2a_op *op = new b2a_op();
+  op->ctx = ctx;
+  op->dtype = dtype;
+  op->kind = OP_CSR;
+  op->n_local = n_rows_local;
+  op->n_global = n_global;
+  op->row_offset = row_offset;
+  op->nnz = nnz;
+  op->lpr = pick_lanes(nnz, n_rows_local);
+  op->d_ptr = const_cast<int64_t *>(d_rowptr);
+  op->d_idx = const_cast<int32_t *>(d_colind);
+  op->d_vals = const_cast<void *>(d_vals);
+  op->owns = false;
+  *out = op;
+  return B2A_OK;
+}
+
+extern "C++" {
+template <class Idx> static inline int64_t host_idx(const void *p, int64_t i, int base) {
+  return (int64_t) reinterpret_cast<const Idx *>(p)[i] - base;
+}
+
+}  // extern "C++"
+
+int b2a_csc_create(b2a_ctx *ctx, int dtype, int64_t n_global, int64_t nnz, const void *colptr, const void *rowval,
+                   const void *nzval, int idx_width, int idx_base, int mode, b2a_op **out) {
+  B2A_TRY(check_op_args(ctx, dtype, n_global, n_global, 0, nnz, idx_width, idx_base));
+  if (!colptr || (nnz > 0 && (!rowval || !nzval)) || !out) return fail(B2A_ERR_ARGUMENT, "NULL array");
+  ARG_CHECK(mode == 0 || mode == 1, "mode must be 0 (transpose at upload) or 1 (scatter kernel)");
+  if (ctx->world > 1) return fail(B2A_ERR_ARGUMENT, "CSC operators are single-GPU; shard rows as CSR");
+  if (mode == 1) {
+    b2a_op *op = new b2a_op();
+    op->ctx = ctx;
+    op->dtype = dtype;
+    op->kind = OP_CSC_SCATTER;
+    op->n_local = op->n_global = n_global;
+    op->nnz = nnz;
+    op->lpr = std::max(2, pick_lanes(nnz, n_global));
+    int s = op_alloc(ctx, op, n_global);
+    if (s == B2A_OK) s = upload_index(ctx, colptr, n_global + 1, idx_width, idx_base, op->d_ptr, nullptr);
+    if (s == B2A_OK) s = upload_index(ctx, rowval, nnz, idx_width, idx_base, nullptr, op->d_idx);
+    if (s == B2A_OK && nnz > 0) {
+      cudaError_t e = cudaMemcpyAsync(op->d_vals, nzval, (size_t)nnz * dtype_size(dtype), cudaMemcpyHostToDevice, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      if (e != cudaSuccess) s = fail(B2A_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (s != B2A_OK) {
+      b2a_op_destroy(op);
+      return s;
+    }
+    *out = op;
+    return B2A_OK;
+  }
+  // mode 0: one-time stable transpose to CSR on the host (setup, not the hot path), then upload
+  const size_t es = dtype_size(dtype);
+  std::vector<int64_t> rowptr((size_t)n_global + 1, 0);
+  auto ridx = [&](int64_t i) {
+    return idx_width == 32 ? host_idx<int32_t>(rowval, i, idx_base) : host_idx<int64_t>(rowval, i, idx_base);
+  };
+  auto cptr = [&](int64_t c) {
+    return idx_width == 32 ? host_idx<int32_t>(colptr, c, idx_base) : host_idx<int64_t>(colptr, c, idx_base);
+  };
+  for (int64_t i = 0; i < nnz; ++i) {
+    const int64_t r = ridx(i);
+    if (r < 0 || r >= n_global) return fail(B2A_ERR_ARGUMENT, "row index out of range in CSC input");
+    rowptr[(size_t)r + 1]++;
+  }
+  for (int64_t r = 0; r < n_global; ++r) rowptr[(size_t)r + 1] += rowptr[(size_t)r];
+  std::vector<int64_t> fill(rowptr.begin(), rowptr.end() - 1);
+  std::vector<int32_t> colind((size_t)nnz);
+  std::vector<char> vals((size_t)nnz * es);
+  for (int64_t c = 0; c < n_global; ++c) {
+    const int64_t s = cptr(c), e = cptr(c + 1);
+    for (int64_t i = s; i < e; ++i) {
+      const int64_t dst = fill[(size_t)ridx(i)]++;
+      colind[(size_t)dst] = (int32_t)c;
+      std::memcpy(&vals[(size_t)dst * es], reinterpret_cast<const char *>(nzval) + (size_t)i * es, es);
+    }
+  }
+  return b2a_csr_create(ctx, dtype, n_global, n_global, 0, nnz, rowptr.data(), colind.data(), vals.data(), 64, 0, out);
+}
+
+int b2a_op_from_callback(b2a_ctx *ctx, int dtype, int64_t n_rows_local, int64_t n_global, b2a_matvec_fn matvec,
+                         void *user, b2a_op **out) {
+  B2A_TRY(check_op_args(ctx, dtype, n_rows_local, n_global, 0, 0, 32, 0));
+  if (!matvec || !out) return fail(B2A_ERR_ARGUMENT, "NULL callback");
+  b2a_op *op = new b2a_op();
+  op->ctx = ctx;
+  op->dtype = dtype;
+  op->kind = OP_CALLBACK;
+  op->n_local = n_rows_local;
+  op->n_global = n_global;
+  op->fn = matvec;
+  op->user = user;
+  op->owns = false;
+  *out = op;
+  return B2A_OK;
+}
+
+int b2a_op_bytes(b2a_op *op, double *bytes) {
+  if (!op || !bytes) return fail(B2A_ERR_ARGUMENT, "NULL argument");
+  *bytes = eng::op_bytes(op);
+  return B2A_OK;
+}
+
+// ------------------------------------------------------------------------- workspace
+int b2a_ws_destroy(b2a_ws *ws) {
+  if (!ws) return B2A_OK;
+  cudaSetDevice(ws->ctx->device);
+  void *ptrs[] = {ws->dV, ws->dH, ws->dinfo, ws->hb1, ws->hb2, ws->w2sq, ws->partials, ws->partials2, ws->state, ws->dQ, ws->xfull};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  if (ws->pinned) cudaFreeHost(ws->pinned);
+  delete ws;
+  return B2A_OK;
+}
+
+static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_global, int64_t row_offset, int maxdim,
+                          b2a_ws *ws) {
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const size_t es = dtype_size(dtype);
+  ws->ctx = ctx;
+  ws->dtype = dtype;
+  ws->esz = es;
+  ws->n_local = n_local;
+  ws->n_global = n_global;
+  ws->row_offset = row_offset;
+  ws->maxdim = maxdim;
+  const int m1 = maxdim + 1;
+  ws->all_offsets.assign(ctx->world, 0);
+  ws->all_counts.assign(ctx->world, n_local);
+  int64_t ld_rows = n_local;
+  if (ctx->world > 1) {
+    // share the row partition; uniform blocks (all but the last rank equal) use all-gather
+    int64_t *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, sizeof(int64_t) * 2 * (ctx->world + 1)));
+    int64_t mine[2] = {row_offset, n_local};
+    CUDA_TRY(cudaMemcpyAsync(d, mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_TRY(g_nccl.AllGather(d, d + 2, 2, ncclInt64, ctx->comm, ctx->stream));
+    std::vector<int64_t> all(2 * ctx->world);
+    CUDA_TRY(cudaMemcpyAsync(all.data(), d + 2, sizeof(int64_t) * 2 * ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    int64_t expect = 0;
+    const int64_t blk = all[1];
+    ws->uniform_partition = true;
+    for (int r = 0; r < ctx->world; ++r) {
+      ws->all_offsets[r] = all[2 * r];
+      ws->all_counts[r] = all[2 * r + 1];
+      if (all[2 * r] != expect) return fail(B2A_ERR_ARGUMENT, "row blocks of the ranks must be contiguous and ordered");
+      expect += all[2 * r + 1];
+      if (r + 1 < ctx->world && all[2 * r + 1] != blk) ws->uniform_partition = false;
+      if (r + 1 == ctx->world && all[2 * r + 1] > blk) ws->uniform_partition = false;
+    }
+    if (expect != n_global) return fail(B2A_ERR_DIMENSION, "row blocks do not add up to n_global");
+    if (ws->uniform_partition) ld_rows = std::max(ld_rows, blk);  // all-gather reads blk rows from every rank
+  }
+  ws->ld = round_up(std::max<int64_t>(ld_rows, 1), 16);
+  CUDA_TRY(cudaMalloc(&ws->dV, (size_t)ws->ld * m1 * es));
+  CUDA_TRY(cudaMemsetAsync(ws->dV, 0, (size_t)ws->ld * m1 * es, ctx->stream));  // padding rows stay zero forever
+  ws->H.assign((size_t)m1 * maxdim * es, 0);
+  ws->Q.assign((size_t)maxdim * maxdim * es, 0);
+  ws->dots_grid_max = 2 * ctx->num_sms;
+  ws->upd_grid_max = 8 * ctx->num_sms;
+  CUDA_TRY(cudaMalloc(&ws->dH, (size_t)m1 * maxdim * es));
+  CUDA_TRY(cudaMemsetAsync(ws->dH, 0, (size_t)m1 * maxdim * es, ctx->stream));
+  CUDA_TRY(cudaMalloc(&ws->dinfo, sizeof(int) * (m1 + 1)));
+  CUDA_TRY(cudaMemsetAsync(ws->dinfo, 0, sizeof(int) * (m1 + 1), ctx->stream));
+  CUDA_TRY(cudaMalloc(&ws->hb1, (size_t)(m1 + 1) * es + 16));
+  CUDA_TRY(cudaMalloc(&ws->hb2, (size_t)(m1 + 1) * es + 16));
+  CUDA_TRY(cudaMemsetAsync(ws->hb1, 0, (size_t)(m1 + 1) * es + 16, ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(ws->hb2, 0, (size_t)(m1 + 1) * es + 16, ctx->stream));
+  CUDA_TRY(cudaMalloc(&ws->w2sq, 16));
+  CUDA_TRY(cudaMemsetAsync(ws->w2sq, 0, 16, ctx->stream));
+  CUDA_TRY(cudaMalloc(&ws->partials, (size_t)(66) * ws->dots_grid_max * es));
+  CUDA_TRY(cudaMalloc(&ws->partials2, sizeof(double) * ws->upd_grid_max));
+  CUDA_TRY(cudaMalloc(&ws->state, sizeof(b2a::SweepState)));
+  CUDA_TRY(cudaMemsetAsync(ws->state, 0, sizeof(b2a::SweepState), ctx->stream));
+  CUDA_TRY(cudaMalloc(&ws->dQ, (size_t)std::max(maxdim * maxdim, 1) * es));
+  if (ctx->world > 1) {
+    const int64_t nx = ws->uniform_partition ? ws->all_counts[0] * ctx->world : n_global;
+    CUDA_TRY(cudaMalloc(&ws->xfull, (size_t)nx * es));
+  }
+  ws->pinned_bytes = (size_t)m1 * maxdim * es + sizeof(int) * (m1 + 1) + sizeof(b2a::SweepState) + 64;
+  CUDA_TRY(cudaMallocHost(&ws->pinned, ws->pinned_bytes));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return B2A_OK;
+}
+
+int b2a_ws_create(b2a_ctx *ctx, int dtype, int64_t n_rows_local, int64_t n_global, int64_t row_offset, int maxdim,
+                  b2a_ws **out) {
+  if (!ctx || !out) return fail(B2A_ERR_ARGUMENT, "NULL argument");
+  ARG_CHECK(dtype == B2A_F64 || dtype == B2A_C64, "dtype must be B2A_F64 or B2A_C64");
+  ARG_CHECK(n_rows_local >= 0 && n_global >= 1 && row_offset >= 0 && row_offset + n_rows_local <= n_global,
+            "bad row block");
+  ARG_CHECK(maxdim >= 1, "Krylov dimension must be positive");
+  // ArnoldiMethod.jl:62-63
+  ARG_CHECK((int64_t)maxdim <= n_global, "Krylov dimension should be less than matrix order.");
+  b2a_ws *ws = new b2a_ws();
+  int s = ws_create_impl(ctx, dtype, n_rows_local, n_global, row_offset, maxdim, ws);
+  if (s != B2A_OK) {
+    b2a_ws_destroy(ws);
+    return s;
+  }
+  *out = ws;
+  return B2A_OK;
+}
+
+#define WS_COL_CHECK(ws, j) \
+  ARG_CHECK((ws) && (j) >= 1 && (j) <= (ws)->maxdim + 1, "column index out of range")
+
+int b2a_ws_set_col(b2a_ws *ws, int j, const void *host) {
+  WS_COL_CHECK(ws, j);
+  if (!host) return fail(B2A_ERR_ARGUMENT, "NULL host pointer");
+  char *dst = reinterpret_cast<char *>(ws->dV) + (size_t)(j - 1) * ws->ld * ws->esz;
+  CUDA_TRY(cudaMemcpyAsync(dst, host, (size_t)ws->n_local * ws->esz, cudaMemcpyHostToDevice, ws->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ws->ctx->stream));
+  return B2A_OK;
+}
+int b2a_ws_set_col_device(b2a_ws *ws, int j, const void *dev) {
+  WS_COL_CHECK(ws, j);
+  if (!dev) return fail(B2A_ERR_ARGUMENT, "NULL device pointer");
+  char *dst = reinterpret_cast<char *>(ws->dV) + (size_t)(j - 1) * ws->ld * ws->esz;
+  CUDA_TRY(cudaMemcpyAsync(dst, dev, (size_t)ws->n_local * ws->esz, cudaMemcpyDeviceToDevice, ws->ctx->stream));
+  return B2A_OK;
+}
+int b2a_ws_get_cols(b2a_ws *ws, int j0, int ncols, void *host, int64_t ld) {
+  if (ncols == 0) return B2A_OK;
+  WS_COL_CHECK(ws, j0);
+  ARG_CHECK(ncols > 0 && j0 + ncols - 1 <= ws->maxdim + 1, "column range out of bounds");
+  ARG_CHECK(host && ld >= ws->n_local, "bad host matrix");
+  const char *src = reinterpret_cast<const char *>(ws->dV) + (size_t)(j0 - 1) * ws->ld * ws->esz;
+  CUDA_TRY(cudaMemcpy2DAsync(host, (size_t)ld * ws->esz, src, (size_t)ws->ld * ws->esz, (size_t)ws->n_local * ws->esz,
+                             ncols, cudaMemcpyDeviceToHost, ws->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ws->ctx->stream));
+  return B2A_OK;
+}
+int b2a_ws_col_ptr(b2a_ws *ws, int j, void **dev, int64_t *ld) {
+  WS_COL_CHECK(ws, j);
+  if (dev) *dev = reinterpret_cast<char *>(ws->dV) + (size_t)(j - 1) * ws->ld * ws->esz;
+  if (ld) *ld = ws->ld;
+  return B2A_OK;
+}
+int b2a_ws_host_arrays(b2a_ws *ws, void **H, int *ldh, void **Q, int *ldq) {
+  if (!ws) return fail(B2A_ERR_ARGUMENT, "NULL ws");
+  if (H) *H = ws->H.data();
+  if (ldh) *ldh = ws->maxdim + 1;
+  if (Q) *Q = ws->Q.data();
+  if (ldq) *ldq = ws->maxdim;
+  return B2A_OK;
+}
+
+// -------------------------------------------------------------------------- hot path
+int b2a_reinitialize(b2a_ws *ws, int j, int mode, uint64_t seed, int *ok) {
+  ARG_CHECK(ws && j >= 0 && j <= ws->maxdim, "column index out of range");
+  ARG_CHECK(mode == B2A_INIT_RAND || mode == B2A_INIT_KEEP, "mode must be B2A_INIT_RAND or B2A_INIT_KEEP");
+  CUDA_TRY(cudaSetDevice(ws->ctx->device));
+  return ws->dtype == B2A_F64 ? eng::reinitialize<double>(ws, j, mode, seed, ok, nullptr)
+                              : eng::reinitialize<cplx>(ws, j, mode, seed, ok, nullptr);
+}
+
+extern "C++" {
+template <class HT> static int orthogonalize_impl(b2a_ws *ws, int j, void *h_host, int *ok) {
+  using DT = typename Dev<HT>::type;
+  const int m1 = ws->maxdim + 1;
+  B2A_TRY((eng::enqueue_cgs<DT>(ws, j, 0, j)));
+  CUDA_TRY(cudaMemcpyAsync(ws->pinned, reinterpret_cast<char *>(ws->dH) + (size_t)(j - 1) * m1 * sizeof(HT),
+                           (size_t)(j + 1) * sizeof(HT), cudaMemcpyDeviceToHost, ws->ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(ws->pinned + (size_t)m1 * sizeof(HT), ws->dinfo + j, sizeof(int), cudaMemcpyDeviceToHost,
+                           ws->ctx->stream));
+  CUDA_TRY(cudaMemsetAsync(&ws->state->poison, 0, sizeof(int), ws->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ws->ctx->stream));
+  HT *H = reinterpret_cast<HT *>(ws->H.data());
+  std::memcpy(H + (size_t)(j - 1) * m1, ws->pinned, (size_t)(j + 1) * sizeof(HT));
+  if (h_host) std::memcpy(h_host, ws->pinned, (size_t)(j + 1) * sizeof(HT));
+  int info;
+  std::memcpy(&info, ws->pinned + (size_t)m1 * sizeof(HT), sizeof(int));
+  if (ok) *ok = (info & 2) ? 0 : 1;
+  return B2A_OK;
+}
+
+}  // extern "C++"
+
+int b2a_orthogonalize(b2a_ws *ws, int j, void *h_host, int *ok) {
+  ARG_CHECK(ws && j >= 1 && j <= ws->maxdim, "column index out of range");
+  CUDA_TRY(cudaSetDevice(ws->ctx->device));
+  return ws->dtype == B2A_F64 ? orthogonalize_impl<double>(ws, j, h_host, ok)
+                              : orthogonalize_impl<cplx>(ws, j, h_host, ok);
+}
+
+static int check_ws_op(b2a_ws *ws, b2a_op *A) {
+  if (!ws || !A) return fail(B2A_ERR_ARGUMENT, "NULL handle");
+  ARG_CHECK(ws->ctx == A->ctx, "workspace and operator belong to different contexts");
+  ARG_CHECK(ws->dtype == A->dtype, "workspace and operator have different element types");
+  if (ws->n_global != A->n_global || ws->n_local != A->n_local)
+    return fail(B2A_ERR_DIMENSION, "workspace and operator dimensions differ");
+  return B2A_OK;
+}
+
+int b2a_ws_matvec(b2a_ws *ws, b2a_op *A, int jsrc, int jdst) {
+  B2A_TRY(check_ws_op(ws, A));
+  WS_COL_CHECK(ws, jsrc);
+  WS_COL_CHECK(ws, jdst);
+  ARG_CHECK(jsrc != jdst, "source and destination columns must differ");
+  CUDA_TRY(cudaSetDevice(ws->ctx->device));
+  if (ws->dtype == B2A_F64) return eng::enqueue_matvec<double>(ws, A, jsrc - 1, jdst - 1);
+  return eng::enqueue_matvec<cdouble>(ws, A, jsrc - 1, jdst - 1);
+}
+
+int b2a_iterate_arnoldi(b2a_ws *ws, b2a_op *A, int from, int to, uint64_t seed, void *H_host, int ldh,
+                        b2a_stats *stats) {
+  B2A_TRY(check_ws_op(ws, A));
+  ARG_CHECK(from >= 1 && to <= ws->maxdim, "step range out of bounds");
+  CUDA_TRY(cudaSetDevice(ws->ctx->device));
+  b2a_stats local{};
+  b2a_stats *st = stats ? stats : &local;
+  if (from <= to) {
+    B2A_TRY(ws->dtype == B2A_F64 ? eng::iterate_arnoldi<double>(ws, A, from, to, seed, st)
+                                 : eng::iterate_arnoldi<cplx>(ws, A, from, to, seed, st));
+  }
+  if (H_host && from <= to) {
+    ARG_CHECK(ldh >= ws->maxdim + 1, "ldh too small");
+    const int m1 = ws->maxdim + 1;
+    for (int s = from; s <= to; ++s)
+      std::memcpy(reinterpret_cast<char *>(H_host) + (size_t)(s - 1) * ldh * ws->esz,
+                  ws->H.data() + (size_t)(s - 1) * m1 * ws->esz, (size_t)(s + 1) * ws->esz);
+  }
+  return B2A_OK;
+}
+
+int b2a_rotate_basis(b2a_ws *ws, int purge, int k, int maxdim, const void *Q_host, int ldq, b2a_stats *stats) {
+  if (!ws) return fail(B2A_ERR_ARGUMENT, "NULL ws");
+  ARG_CHECK(maxdim >= 1 && maxdim <= ws->maxdim && purge >= 1 && purge <= k && k <= maxdim, "bad (purge, k, maxdim)");
+  if (!Q_host) {
+    Q_host = ws->Q.data();
+    ldq = ws->maxdim;
+  }
+  ARG_CHECK(ldq >= maxdim, "ldq too small");
+  CUDA_TRY(cudaSetDevice(ws->ctx->device));
+  return ws->dtype == B2A_F64
+             ? drv::rotate_basis<double>(ws, purge, k, maxdim, reinterpret_cast<const double *>(Q_host), ldq, stats)
+             : drv::rotate_basis<cplx>(ws, purge, k, maxdim, reinterpret_cast<const cplx *>(Q_host), ldq, stats);
+}
+
+int b2a_rotate_final(b2a_ws *ws, int nconv, const void *Q_host, int ldq, b2a_stats *stats) {
+  if (!ws) return fail(B2A_ERR_ARGUMENT, "NULL ws");
+  ARG_CHECK(nconv >= 0 && nconv <= ws->maxdim, "bad nconv");
+  if (!Q_host) {
+    Q_host = ws->Q.data();
+    ldq = ws->maxdim;
+  }
+  ARG_CHECK(ldq >= nconv, "ldq too small");
+  CUDA_TRY(cudaSetDevice(ws->ctx->device));
+  return ws->dtype == B2A_F64
+             ? drv::rotate_final<double>(ws, nconv, reinterpret_cast<const double *>(Q_host), ldq, stats)
+             : drv::rotate_final<cplx>(ws, nconv, reinterpret_cast<const cplx *>(Q_host), ldq, stats);
+}
+
+int b2a_basis_times(b2a_ws *ws, int nconv, const double *Y, int ldy, double *X, int64_t ldx) {
+  if (!ws) return fail(B2A_ERR_ARGUMENT, "NULL ws");
+  if (nconv == 0) return B2A_OK;
+  ARG_CHECK(nconv >= 1 && nconv <= ws->maxdim + 1 && Y && X && ldy >= nconv && ldx >= ws->n_local, "bad arguments");
+  b2a_ctx *ctx = ws->ctx;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  std::vector<cplx> Yp((size_t)nconv * nconv);
+  for (int o = 0; o < nconv; ++o)
+    for (int c = 0; c < nconv; ++c) Yp[(size_t)o * nconv + c] = cplx(Y[2 * ((size_t)o * ldy + c)], Y[2 * ((size_t)o * ldy + c) + 1]);
+  cdouble *dY = nullptr, *dX = nullptr;
+  const int64_t n = ws->n_local;
+  CUDA_TRY(cudaMalloc(&dY, sizeof(cdouble) * nconv * nconv));
+  cudaError_t e = cudaMalloc(&dX, sizeof(cdouble) * (size_t)std::max<int64_t>(n, 1) * nconv);
+  if (e != cudaSuccess) {
+    cudaFree(dY);
+    CUDA_TRY(e);
+  }
+  e = cudaMemcpyAsync(dY, Yp.data(), sizeof(cdouble) * nconv * nconv, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ctx->num_sms * 8, cdiv(n, 256)));
+    if (ws->dtype == B2A_F64)
+      b2a::basis_times_kernel<double><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const double *>(ws->dV), ws->ld, n, nconv, nconv, dY, dX, n);
+    else
+      b2a::basis_times_kernel<cdouble><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const cdouble *>(ws->dV), ws->ld, n, nconv, nconv, dY, dX, n);
+    ctx->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess)
+    e = cudaMemcpy2DAsync(X, (size_t)ldx * 16, dX, (size_t)n * 16, (size_t)n * 16, nconv, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dY);
+  cudaFree(dX);
+  CUDA_TRY(e);
+  return B2A_OK;
+}
+
+// ------------------------------------------------------------------- whole restart loop
+int b2a_partialschur(b2a_ws *ws, b2a_op *A, const b2a_params *p, b2a_history *history, double *eigenvalues_c64) {
+  B2A_TRY(check_ws_op(ws, A));
+  if (!p || !history) return fail(B2A_ERR_ARGUMENT, "NULL params / history");
+  const int64_t n = ws->n_global;
+  const int vcols = ws->maxdim + 1;  // size(arnoldi.V, 2)
+  // defaults of src/run.jl:152-163
+  const int nev = p->nev != 0 ? p->nev : (int)std::min<int64_t>(6, n);
+  const int mindim = p->mindim != 0 ? p->mindim : (int)std::min<int64_t>(std::min<int64_t>(std::max(10, nev), n), vcols - 1);
+  const int maxdim = p->maxdim != 0 ? p->maxdim : (int)std::min<int64_t>(std::min<int64_t>(std::max(20, 2 * nev), n), vcols - 1);
+  const double tol = p->tol >= 0 ? p->tol : std::sqrt(b2a::host::kEps);
+  const int restarts = p->restarts >= 0 ? p->restarts : 200;
+  const int start_from = p->start_from > 0 ? p->start_from : 1;
+  const int initialize = p->initialize >= 0 ? p->initialize : (start_from == 1 ? B2A_INIT_RAND : B2A_INIT_NONE);
+  // src/run.jl:165-174
+  ARG_CHECK(nev >= 1, "nev cannot be less than 1");
+  if (!(nev <= mindim && mindim <= maxdim && (int64_t)maxdim <= n))
+    return fail(B2A_ERR_ARGUMENT, "nev <= mindim <= maxdim <= size(A, 1) does not hold, got " + std::to_string(nev) +
+                                      " <= " + std::to_string(mindim) + " <= " + std::to_string(maxdim) + " <= " +
+                                      std::to_string(n));
+  ARG_CHECK(maxdim < vcols, "maxdim should be strictly less than size(arnoldi.V, 2)");
+  ARG_CHECK(1 <= start_from && start_from <= maxdim, "start_from should be between 1 and maxdim");
+  ARG_CHECK(p->which >= B2A_LM && p->which <= B2A_SI, "Unknown target");
+  ARG_CHECK(initialize >= B2A_INIT_NONE && initialize <= B2A_INIT_KEEP, "bad initialize mode");
+  CUDA_TRY(cudaSetDevice(ws->ctx->device));
+
+  std::memset(history, 0, sizeof(*history));
+  const int m1 = ws->maxdim + 1;
+  // fill!(view(H, :, start_from:end), 0)   (run.jl:176)
+  std::memset(ws->H.data() + (size_t)(start_from - 1) * m1 * ws->esz, 0, (size_t)(ws->maxdim - start_from + 1) * m1 * ws->esz);
+  if (initialize != B2A_INIT_NONE) {
+    int ok;
+    B2A_TRY(ws->dtype == B2A_F64 ? eng::reinitialize<double>(ws, start_from - 1, initialize, p->seed, &ok, &history->stats)
+                                 : eng::reinitialize<cplx>(ws, start_from - 1, initialize, p->seed, &ok, &history->stats));
+  }
+  try {
+    if (ws->dtype == B2A_F64)
+      return drv::partialschur<double>(ws, A, mindim, maxdim, nev, tol, restarts, p->which, start_from, p->seed, history, eigenvalues_c64);
+    return drv::partialschur<cplx>(ws, A, mindim, maxdim, nev, tol, restarts, p->which, start_from, p->seed, history, eigenvalues_c64);
+  } catch (const std::exception &e) {
+    return fail(B2A_ERR_INTERNAL, e.what());
+  }
+}
+
+// ------------------------------------------------------------------ host-only algebra
+int b2a_host_local_schurfact(int dtype, void *H, int ldh, int rows, int cols, int from, int to, void *Q, int ldq, int qrows) {
+  using namespace b2a::host;
+  ARG_CHECK(H && rows >= 1 && cols >= 1 && ldh >= rows && from >= 1 && to <= cols && to <= rows, "bad arguments");
+  try {
+    if (dtype == B2A_F64) {
+      Mat<double> Hm{(double *)H, rows, cols, ldh}, Qm{(double *)Q, qrows, cols, ldq};
+      return local_schurfact(Hm, from, to, Qm) ? B2A_OK : B2A_ERR_QR;
+    }
+    Mat<cplx> Hm{(cplx *)H, rows, cols, ldh}, Qm{(cplx *)Q, qrows, cols, ldq};
+    return local_schurfact(Hm, from, to, Qm) ? B2A_OK : fail(B2A_ERR_QR, "QR algorithm did not converge");
+  } catch (const QRNoConvergence &e) {
+    return fail(B2A_ERR_QR, e.what());
+  }
+}
+
+extern "C++" {
+template <class HT>
+static int host_restart_impl(void *H, int ldh, void *Q, int ldq, int maxdim, int mindim, int nev, double tol, int which,
+                             int active, int *k, int *purge, int *nlock, double *eig, double *res) {
+  using namespace b2a::host;
+  Mat<HT> Hm{(HT *)H, maxdim + 1, maxdim, ldh}, Qm{(HT *)Q, maxdim, maxdim, ldq};
+  RestartScratch<HT> S(maxdim);
+  RestartPlan plan;
+  try {
+    plan = restart_decision(Hm, Qm, maxdim, mindim, nev, tol, Ordering{which}, active, S);
+  } catch (const QRNoConvergence &e) {
+    return fail(B2A_ERR_QR, e.what());
+  }
+  if (k) *k = plan.k;
+  if (purge) *purge = plan.purge;
+  if (nlock) *nlock = plan.nlock;
+  for (int i = 0; i < maxdim; ++i) {
+    if (eig) {
+      eig[2 * i] = S.lams[i].real();
+      eig[2 * i + 1] = S.lams[i].imag();
+    }
+    if (res) res[i] = S.rs[i];
+  }
+  return B2A_OK;
+}
+
+}  // extern "C++"
+
+int b2a_host_restart(int dtype, void *H, int ldh, void *Q, int ldq, int maxdim, int mindim, int nev, double tol,
+                     int which, int active, int *k, int *purge, int *nlock, double *eigenvalues_c64, double *residuals) {
+  ARG_CHECK(H && Q && maxdim >= 1 && ldh >= maxdim + 1 && ldq >= maxdim, "bad arguments");
+  ARG_CHECK(nev >= 1 && nev <= mindim && mindim <= maxdim && active >= 1 && active <= maxdim, "bad dimensions");
+  ARG_CHECK(which >= B2A_LM && which <= B2A_SI, "Unknown target");
+  return dtype == B2A_F64 ? host_restart_impl<double>(H, ldh, Q, ldq, maxdim, mindim, nev, tol, which, active, k, purge, nlock, eigenvalues_c64, residuals)
+                          : host_restart_impl<cplx>(H, ldh, Q, ldq, maxdim, mindim, nev, tol, which, active, k, purge, nlock, eigenvalues_c64, residuals);
+}
+
+int b2a_host_sortschur(int dtype, void *H, int ldh, void *Q, int ldq, int maxdim, int nconv, int which) {
+  using namespace b2a::host;
+  ARG_CHECK(H && Q && maxdim >= 1 && ldh >= maxdim + 1 && ldq >= maxdim && nconv >= 0 && nconv <= maxdim, "bad arguments");
+  ARG_CHECK(which >= B2A_LM && which <= B2A_SI, "Unknown target");
+  if (dtype == B2A_F64) {
+    Mat<double> Hm{(double *)H, maxdim + 1, maxdim, ldh}, Qm{(double *)Q, maxdim, maxdim, ldq};
+    for (int j = 1; j <= maxdim; ++j)
+      for (int i = 1; i <= maxdim; ++i) Qm(i, j) = (i == j) ? 1.0 : 0.0;
+    sortschur(Hm, Qm, nconv, Ordering{which});
+  } else {
+    Mat<cplx> Hm{(cplx *)H, maxdim + 1, maxdim, ldh}, Qm{(cplx *)Q, maxdim, maxdim, ldq};
+    for (int j = 1; j <= maxdim; ++j)
+      for (int i = 1; i <= maxdim; ++i) Qm(i, j) = (i == j) ? cplx(1.0) : cplx(0.0);
+    sortschur(Hm, Qm, nconv, Ordering{which});
+  }
+  return B2A_OK;
+}
+
+int b2a_host_givens(int dtype, const double *f, const double *g, double *c, double *s, double *r) {
+  using namespace b2a::host;
+  if (!f || !g || !c || !s || !r) return fail(B2A_ERR_ARGUMENT, "NULL argument");
+  if (dtype == B2A_F64) {
+    auto G = givens(f[0], g[0]);
+    *c = G.c;
+    s[0] = G.s;
+    r[0] = G.r;
+  } else {
+    auto G = givens(cplx(f[0], f[1]), cplx(g[0], g[1]));
+    *c = G.c;
+    s[0] = G.s.real();
+    s[1] = G.s.imag();
+    r[0] = G.r.real();
+    r[1] = G.r.imag();
+  }
+  return B2A_OK;
+}
+
+}  // extern "C"

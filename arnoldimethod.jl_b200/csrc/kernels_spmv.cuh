@@ -1,0 +1,154 @@
+// kernels_spmv.cuh - sparse mat-vec y = A x for the operator call of the Arnoldi step
+// (`mul!(view(V,:,j+1), A, view(V,:,j))`, src/expansion.jl:121; Julia's stdlib does this
+// with a single-threaded CSC loop).
+//
+//   spmv_csr_vector : CSR, LPR lanes per row (LPR = 2..32 chosen from nnz/row at upload),
+//                     coalesced row-segment loads of (colind, vals), gathers of x through
+//                     the read-only path, warp-shuffle partial sums, U rows in flight per
+//                     lane group for memory-level parallelism.  Deterministic.
+//   spmv_csr_scalar : one thread per row (nnz/row <= ~2, e.g. diagonal operators).
+//   spmv_csc_scatter: Julia's native CSC layout without a transpose: one lane group per
+//                     COLUMN, y[row] += val * x[col] with red.global.add.f64 (result sums
+//                     in arrival order - not bit-reproducible; mode 1 of b2a_csc_create).
+//
+// Algorithmic bytes per launch: nnz (s + 4) + 8 (n + 1) + 2 n s.
+#pragma once
+
+#include "device_common.cuh"
+
+namespace b2a {
+
+template <class T> __device__ __forceinline__ T ld_ro(const T *p);
+template <> __device__ __forceinline__ double ld_ro<double>(const double *p) { return __ldg(p); }
+template <> __device__ __forceinline__ cdouble ld_ro<cdouble>(const cdouble *p) { return __ldg(p); }
+
+template <class T, int LPR> __device__ __forceinline__ T group_sum(T v);
+template <int LPR> __device__ __forceinline__ double group_sum_d(double v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <class T, int LPR, int U>
+__global__ void __launch_bounds__(256)
+    spmv_csr_vector_kernel(int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                           const T *__restrict__ vals, const T *__restrict__ x, T *__restrict__ y,
+                           const int *poison) {
+  if (*poison) return;
+  const int sub = threadIdx.x & (LPR - 1);
+  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / LPR;
+
+  for (int64_t rbase = group; rbase < n_rows; rbase += ngroups * U) {
+    int64_t rs[U], re[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = rbase + (int64_t)u * ngroups;
+      if (r < n_rows) {
+        rs[u] = __ldg(rowptr + r);
+        re[u] = __ldg(rowptr + r + 1);
+      } else {
+        rs[u] = re[u] = 0;
+      }
+    }
+    // first LPR entries of each of the U rows: all loads issued before any use
+    int32_t c[U];
+    T a[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = rs[u] + sub;
+      const bool ok = i < re[u];
+      c[u] = ok ? __ldg(colind + i) : 0;
+      a[u] = ok ? ld_ro<T>(vals + i) : Scalar<T>::zero();
+    }
+    T acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = rs[u] + sub < re[u];
+      const T xv = ok ? ld_ro<T>(x + c[u]) : Scalar<T>::zero();
+      acc[u] = Scalar<T>::mul(a[u], xv);
+    }
+    // rows longer than LPR
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      for (int64_t i = rs[u] + sub + LPR; i < re[u]; i += LPR)
+        acc[u] = Scalar<T>::fma_(ld_ro<T>(vals + i), ld_ro<T>(x + __ldg(colind + i)), acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      T s = acc[u];
+      if (Scalar<T>::is_complex) {
+        double2 *sp = reinterpret_cast<double2 *>(&s);
+        sp->x = group_sum_d<LPR>(sp->x);
+        sp->y = group_sum_d<LPR>(sp->y);
+      } else {
+        double *sp = reinterpret_cast<double *>(&s);
+        *sp = group_sum_d<LPR>(*sp);
+      }
+      const int64_t r = rbase + (int64_t)u * ngroups;
+      if (sub == 0 && r < n_rows) y[r] = s;
+    }
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256)
+    spmv_csr_scalar_kernel(int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                           const T *__restrict__ vals, const T *__restrict__ x, T *__restrict__ y,
+                           const int *poison) {
+  if (*poison) return;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+    const int64_t s = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
+    T acc = Scalar<T>::zero();
+    for (int64_t i = s; i < e; ++i) acc = Scalar<T>::fma_(ld_ro<T>(vals + i), ld_ro<T>(x + __ldg(colind + i)), acc);
+    y[r] = acc;
+  }
+}
+
+// ---- CSC scatter (K2) ----------------------------------------------------------
+__device__ __forceinline__ void red_add(double *p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) zero_vector_kernel(T *__restrict__ y, int64_t n, const int *poison) {
+  if (*poison) return;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) y[r] = Scalar<T>::zero();
+}
+
+template <class T, int LPC>
+__global__ void __launch_bounds__(256)
+    spmv_csc_scatter_kernel(int64_t n_cols, const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowind,
+                            const T *__restrict__ vals, const T *__restrict__ x, T *__restrict__ y,
+                            const int *poison) {
+  if (*poison) return;
+  const int sub = threadIdx.x & (LPC - 1);
+  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPC;
+  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / LPC;
+  for (int64_t col = group; col < n_cols; col += ngroups) {
+    const int64_t s = __ldg(colptr + col), e = __ldg(colptr + col + 1);
+    const T xv = ld_ro<T>(x + col);
+    for (int64_t i = s + sub; i < e; i += LPC) {
+      const T p = Scalar<T>::mul(ld_ro<T>(vals + i), xv);
+      double *dst = reinterpret_cast<double *>(y + __ldg(rowind + i));
+      if (Scalar<T>::is_complex) {
+        const double2 *pp = reinterpret_cast<const double2 *>(&p);
+        red_add(dst, pp->x);
+        red_add(dst + 1, pp->y);
+      } else {
+        red_add(dst, *reinterpret_cast<const double *>(&p));
+      }
+    }
+  }
+}
+
+// ---- one-time CSC -> CSR transpose on the device (mode 0 of b2a_csc_create) ----
+__global__ void count_rows_kernel(int64_t nnz, const int32_t *__restrict__ rowind, unsigned long long *counts) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride)
+    atomicAdd(counts + rowind[i], 1ull);
+}
+
+}  // namespace b2a

@@ -1,0 +1,324 @@
+"""GPU parity, end to end: b2a.partialschur (C-ABI b2a_partialschur: CUDA expansion + C++
+restart driver) against the reference's integration tests, its published known answers and
+the oracle run from the same start vector.
+
+Parity definition: same v1 => (i) eigenvalues agree to <= 10 tol |lambda|,
+(ii) ||AQ - QR|| within the reference test bounds, (iii) ||Q'Q - I|| < 1000 eps,
+(iv) mvproducts within one restart's worth (maxdim - mindim) of the oracle.
+"""
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import b200arnoldi as b2a
+import oracle
+from oracle import dense_small as ds
+
+pytestmark = pytest.mark.gpu
+
+EPS = np.finfo(np.float64).eps
+TYPES = [np.float64, np.complex128]
+README_EIGS = np.array([
+    0.0009674354160236865, 0.003868805732811139, 0.008701304061962657, 0.01546025527344699,
+    0.024139120518486677, 0.0347295035554728, 0.04722115887278571, 0.06160200160067088,
+    0.0778581192025522, 0.09597378493453936,
+])
+
+
+def rand(rng, T, *shape):
+    if T is np.complex128:
+        return rng.random(shape) + 1j * rng.random(shape)
+    return rng.random(shape)
+
+
+def tridiag(n):
+    return sp.diags([-np.ones(n - 1), 2 * np.ones(n), -np.ones(n - 1)], [-1, 0, 1], format="csr")
+
+
+def match_eigs(a, b, tol):
+    a, b = list(np.asarray(a)), list(np.asarray(b))
+    assert len(a) == len(b)
+    for x in a:
+        j = int(np.argmin([abs(x - y) for y in b]))
+        assert abs(x - b[j]) <= tol * max(1.0, abs(x)), (x, b[j])
+        b.pop(j)
+
+
+# ------------------------------------------------------------- README known answer
+@pytest.mark.parametrize("layout", ["csr", "csc"])
+def test_readme_example(layout):
+    A = tridiag(100).asformat(layout)
+    rng = np.random.default_rng(0)
+    v1 = rng.random(100)
+    P, hist = b2a.partialschur(A, nev=10, tol=1e-6, which="SR", v1=v1)
+    assert hist.converged and hist.nconverged == 10
+    assert np.allclose(np.sort(P.eigenvalues.real), README_EIGS, rtol=0, atol=1e-11)  # readme.md:40-49
+    assert np.all(P.eigenvalues.imag == 0)
+    assert 150 <= hist.mvproducts <= 200  # readme.md:52 (174 for an unrecorded random start)
+    Q, R = P.Q, P.R
+    assert 1e-9 < np.linalg.norm(A @ Q - Q @ R) < 1e-6  # readme.md:54-55: 6.4e-8
+    assert np.linalg.norm(Q.T @ Q - np.eye(10)) < 1000 * EPS
+    vals, X = b2a.partialeigen(P)
+    assert np.linalg.norm(A @ X - X @ np.diag(vals)) < 1e-6  # readme.md:59-60
+    # the oracle from the same start vector takes the same path
+    Po, ho = oracle.partialschur(A, v1=v1, nev=10, tol=1e-6, which="SR")
+    assert abs(hist.mvproducts - ho.mvproducts) <= 10
+    match_eigs(P.eigenvalues, Po.eigenvalues, 1e-5)
+
+
+def test_readme_example_random_start():
+    counts = []
+    for seed in range(5):
+        P, hist = b2a.partialschur(tridiag(100), nev=10, tol=1e-6, which="SR", seed=seed)
+        assert hist.converged
+        assert np.allclose(np.sort(P.eigenvalues.real), README_EIGS, rtol=0, atol=1e-11)
+        counts.append(hist.mvproducts)
+    assert 150 <= np.median(counts) <= 200
+
+
+# ---------------------------------------------------------- test/partial_schur.jl
+@pytest.mark.parametrize("T", TYPES)
+def test_low_rank(T):
+    rng = np.random.default_rng(3)
+    A = rand(rng, T, 10, 3)
+    B = A @ A.conj().T
+    P, hist = b2a.partialschur(B, nev=5, mindim=5, maxdim=7, tol=EPS, seed=1)
+    assert hist.converged
+    assert hist.mvproducts == 7
+    Q, R = P.Q, P.R
+    assert np.linalg.norm(Q.conj().T @ Q - np.eye(Q.shape[1])) < 1000 * EPS
+    assert np.linalg.norm(B @ Q - Q @ R) < 1000 * EPS
+    assert np.linalg.norm(np.diag(R)[3:5]) < 1000 * EPS
+
+
+def test_integer_matrix_operates_in_float64():
+    A = (np.random.default_rng(4).random((10, 10)) > 0.5).astype(np.int64)
+    P, _ = b2a.partialschur(A, nev=2, mindim=3, maxdim=8)
+    assert P.Q.dtype == np.float64
+
+
+def test_all_eigenvalues_of_small_matrix():
+    P, hist = b2a.partialschur(np.random.default_rng(5).random((3, 3)))
+    assert hist.converged
+    assert hist.mvproducts == 3
+
+
+def test_incorrect_input():
+    A = np.random.default_rng(6).random((6, 6))
+    with pytest.raises(b2a.DimensionMismatch):
+        b2a.partialschur(np.zeros((4, 3)))
+    for kw in (dict(mindim=5, maxdim=3), dict(nev=5, mindim=3), dict(nev=5, maxdim=3), dict(nev=10), dict(nev=0),
+               dict(which="XX"), dict(v1=np.ones(5))):
+        with pytest.raises(ValueError):
+            b2a.partialschur(A, **kw)
+    # the same checks inside the C ABI (a Julia host would hit these)
+    import ctypes as C
+    from arnoldimethod_jl_b200 import _lib as L
+
+    ctx = b2a.default_context()
+    op = b2a.Operator.from_matrix(ctx, A)
+    ws = b2a.ArnoldiWorkspace(6, 4, ctx=ctx)
+    hist = L.HistoryC()
+    for bad in (dict(nev=5, mindim=3, maxdim=4), dict(nev=2, mindim=3, maxdim=5), dict(nev=-1), dict(which=9),
+                dict(nev=2, mindim=2, maxdim=4, start_from=5)):
+        p = L.Params(nev=0, which=0, tol=-1.0, mindim=0, maxdim=0, restarts=-1, start_from=0, initialize=-1, seed=0)
+        for k, v in bad.items():
+            setattr(p, k, v)
+        assert b2a.lib().b2a_partialschur(ws._h, op._h, C.byref(p), C.byref(hist), None) == L.ERR_ARGUMENT
+    with pytest.raises(ValueError):
+        b2a.ArnoldiWorkspace(6, 7, ctx=ctx)  # ArnoldiMethod.jl:62-63
+
+
+def test_eigenvector_as_initial_vector():
+    rng = np.random.default_rng(7)
+    A = rng.random((30, 30))
+    A = A + A.T
+    lams, X = np.linalg.eigh(A)
+    lam, x = lams[-1], X[:, -1].copy()
+    x0 = x.copy()
+    P, hist = b2a.partialschur(A, v1=x, nev=2, tol=1e-8)
+    assert np.array_equal(x, x0)
+    assert hist.converged
+    assert np.linalg.norm(A @ P.Q - P.Q @ P.R) < 1e-7
+    assert abs(P.eigenvalues.real.max() - lam) < 1e-7
+
+
+def test_target_non_dominant():
+    d = np.concatenate([np.arange(1, 10.05, 0.1), np.arange(50, 54.0)])
+    P, _ = b2a.partialschur(sp.diags(d).tocsr(), which="SR")
+    assert np.all(ds.eigenvalues(P.R).real <= 10)
+
+
+def test_repeated_eigenvalues():
+    d = np.concatenate([np.arange(1, 9.05, 0.1), [9.97, 9.98, 9.99, 10.0, 10.0, 10.0]])
+    A = sp.diags(d).tocsr()
+    P, hist = b2a.partialschur(A, nev=5, maxdim=20, tol=1e-12, seed=9)
+    assert hist.converged
+    assert np.linalg.norm(P.Q.T @ P.Q - np.eye(P.Q.shape[1])) < 100 * EPS
+    assert np.linalg.norm(A @ P.Q - P.Q @ P.R) < A.shape[0] * 1e-12
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_zero_matrix(T):
+    A = np.zeros((5, 5), dtype=T)
+    P, hist = b2a.partialschur(sp.csr_matrix(A))
+    assert hist.converged
+    assert hist.mvproducts == hist.nconverged == 5
+    assert hist.stats["breakdowns"] == 5 - 1 + 1 or hist.stats["breakdowns"] >= 4  # 4 re-initialisations
+    assert np.linalg.norm(P.Q.conj().T @ P.Q - np.eye(5)) < 100 * EPS
+    assert np.linalg.norm(A @ P.Q - P.Q @ P.R) == 0
+
+
+def test_passing_initial_schur_decomposition():
+    """partialschur!(...; start_from) - test/partial_schur.jl:122-138 (resume from a workspace)."""
+    rng = np.random.default_rng(11)
+    A = rng.random((100, 100))
+    arn = b2a.ArnoldiWorkspace(100, 20)
+    F, hist = b2a.partialschur_(A, arn, nev=3, tol=1e-12)
+    assert hist.converged and hist.nconverged in (3, 4)
+    assert np.linalg.norm(A @ F.Q - F.Q @ F.R) < 1e-10
+    F, hist = b2a.partialschur_(A, arn, nev=5, start_from=hist.nconverged + 1, tol=1e-8)
+    assert hist.converged and hist.nconverged in (5, 6)
+    assert np.linalg.norm(A @ F.Q - F.Q @ F.R) < 1e-6
+
+
+def test_conjugate_pair_is_not_split():
+    rng = np.random.default_rng(12)
+    A = rng.standard_normal((200, 200))
+    v1 = rng.random(200)
+    P, hist = b2a.partialschur(A, nev=8, tol=1e-8, which="LM", restarts=400, v1=v1)
+    assert hist.converged and hist.nconverged in (8, 9)
+    lam = P.eigenvalues
+    for z in lam[lam.imag != 0]:
+        assert np.any(lam == z.conjugate())
+    assert np.linalg.norm(A @ P.Q - P.Q @ P.R) < 200 * 1e-8 * abs(lam).max()
+    Po, ho = oracle.partialschur(A, v1=v1, nev=8, tol=1e-8, which="LM", restarts=400)
+    assert hist.nconverged == ho.nconverged
+    assert abs(hist.mvproducts - ho.mvproducts) <= 10
+    match_eigs(lam, Po.eigenvalues, 1e-7)
+
+
+@pytest.mark.parametrize("which", ["LM", "LR", "SR", "LI", "SI"])
+def test_all_targets_complex(which):
+    rng = np.random.default_rng(13)
+    n = 60
+    d = rng.standard_normal(n) * 10 + 10j * rng.standard_normal(n)
+    A = np.diag(d) + 0.01 * (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    v1 = rng.random(n) + 1j * rng.random(n)
+    P, hist = b2a.partialschur(A, nev=4, which=which, tol=1e-9, restarts=500, v1=v1)
+    assert hist.converged
+    ev = np.linalg.eigvals(A)
+    key = {"LM": -abs(ev), "LR": -ev.real, "SR": ev.real, "LI": -ev.imag, "SI": ev.imag}[which]
+    for w in ev[np.argsort(key)[:4]]:
+        assert abs(P.eigenvalues - w).min() < 1e-6
+    Po, ho = oracle.partialschur(A, v1=v1, nev=4, which=which, tol=1e-9, restarts=500)
+    assert hist.mvproducts == ho.mvproducts
+    match_eigs(P.eigenvalues, Po.eigenvalues, 1e-8)
+
+
+# -------------------------------------------------------- test/schur_to_eigen.jl
+@pytest.mark.parametrize("T", TYPES)
+@pytest.mark.parametrize("seed", range(1, 6))
+def test_schur_to_eigen(T, seed):
+    rng = np.random.default_rng(seed)
+    S = sp.random(100, 100, 0.01, random_state=rng)
+    if T is np.complex128:
+        S = S + 1j * sp.random(100, 100, 0.01, random_state=rng)
+    A = (sp.diags(np.arange(1, 101.0)) + S).tocsr().astype(T)
+    eps_ = np.sqrt(EPS)
+    v1 = rand(rng, T, 100)
+    P, hist = b2a.partialschur(A, nev=10, tol=eps_, restarts=200, v1=v1)
+    assert hist.converged
+    vals, vecs = b2a.partialeigen(P)
+    for i in range(10):
+        assert np.linalg.norm(A @ vecs[:, i] - vecs[:, i] * vals[i]) < 2 * eps_ * abs(vals[i])
+    Po, ho = oracle.partialschur(A, v1=v1, nev=10, tol=eps_, restarts=200)
+    assert hist.nconverged == ho.nconverged
+    assert abs(hist.mvproducts - ho.mvproducts) <= 10
+    match_eigs(P.eigenvalues, Po.eigenvalues, 10 * eps_)
+
+
+# ------------------------------------------------- BASELINE-shaped cases (scaled sizes)
+def designed_matrix(rng, T, n, nnz_per_row, ntop):
+    """random CSR with exactly nnz_per_row entries/row, values N(0,1)*0.5/sqrt(nnz),
+    plus a designed top spectrum d_i = 5 + 20*0.9^i on the first ntop diagonal entries."""
+    indptr = np.arange(0, (n + 1) * nnz_per_row, nnz_per_row, dtype=np.int64)
+    indices = rng.integers(0, n, size=n * nnz_per_row).astype(np.int32)
+    vals = rng.standard_normal(n * nnz_per_row) * 0.5 / np.sqrt(nnz_per_row)
+    if T is np.complex128:
+        vals = vals + 1j * rng.standard_normal(n * nnz_per_row) * 0.5 / np.sqrt(nnz_per_row)
+    A = sp.csr_matrix((vals, indices, indptr), shape=(n, n))
+    d = np.zeros(n, dtype=T)
+    d[:ntop] = 5 + 20 * 0.9 ** np.arange(ntop)
+    if T is np.complex128:
+        d[:ntop] = d[:ntop] * np.exp(1j * np.linspace(0, 1.0, ntop))
+    A = (A + sp.diags(d)).tocsr()
+    A.sort_indices()
+    return A
+
+
+@pytest.mark.parametrize("T,n,nnz,nev", [(np.float64, 100000, 16, 20), (np.complex128, 50000, 20, 30)])
+def test_designed_spectrum_converges_like_the_oracle(T, n, nnz, nev):
+    """cfg 2 / cfg 4 shapes at 1/10 - 1/100 scale: converges, residual <= tol |lambda| per pair,
+    same restart path as the oracle from the same start vector."""
+    rng = np.random.default_rng(21)
+    A = designed_matrix(rng, T, n, nnz, 2 * nev)
+    v1 = rand(rng, T, n)
+    tol = 1e-6
+    P, hist = b2a.partialschur(A, nev=nev, which="LM", tol=tol, v1=v1)
+    assert hist.converged
+    Q, R = P.Q, P.R
+    assert np.linalg.norm(Q.conj().T @ Q - np.eye(Q.shape[1])) < 1000 * EPS
+    assert np.linalg.norm(A @ Q - Q @ R) < n * tol  # test/partial_schur.jl:38,105
+    vals, X = b2a.partialeigen(P)
+    for i in range(len(vals)):
+        x = X[:, i] / np.linalg.norm(X[:, i])
+        assert np.linalg.norm(A @ x - vals[i] * x) <= 10 * tol * abs(vals[i])  # docs: ||Ax - x lambda|| < tol |lambda|
+    Po, ho = oracle.partialschur(A, v1=v1, nev=nev, which="LM", tol=tol)
+    assert hist.nconverged == ho.nconverged
+    assert abs(hist.mvproducts - ho.mvproducts) <= (2 * nev - nev)
+    match_eigs(P.eigenvalues, Po.eigenvalues, 10 * tol)
+
+
+def laplacian3d(N):
+    I = sp.identity(N, format="csr")
+    T1 = sp.diags([-np.ones(N - 1), 2 * np.ones(N), -np.ones(N - 1)], [-1, 0, 1], format="csr")
+    return (sp.kron(sp.kron(T1, I), I) + sp.kron(sp.kron(I, T1), I) + sp.kron(sp.kron(I, I), T1)).tocsr()
+
+
+def test_laplacian_largest_eigenvalues():
+    """cfg 3 shape at 48^3: 7-point Laplacian (LPR = 8 kernel, ~100 % second passes).  :LM converges
+    quickly; the eigenvalues are known in closed form."""
+    N = 48
+    A = laplacian3d(N)
+    lam1 = 2 - 2 * np.cos(np.arange(1, N + 1) * np.pi / (N + 1))
+    exact = np.sort((lam1[:, None, None] + lam1[None, :, None] + lam1[None, None, :]).ravel())[::-1]
+    v1 = np.random.default_rng(22).random(N ** 3)
+    P, hist = b2a.partialschur(A, nev=4, which="LM", tol=1e-8, v1=v1, restarts=400)
+    assert hist.converged
+    assert hist.stats["second_passes"] > 0.8 * hist.mvproducts
+    got = np.sort(P.eigenvalues.real)[::-1]
+    assert np.allclose(got[:1], exact[:1], atol=1e-6)  # top eigenvalue is simple
+    assert np.linalg.norm(A @ P.Q - P.Q @ P.R) < 1e-6 * 12
+
+
+def test_full_size_properties():
+    """BASELINE cfg 2 at full size (n = 1e6, 16 nnz/row, maxdim 40): properties that do not need the
+    oracle - Arnoldi relation checked with an independent SciPy mat-vec, orthonormality of V."""
+    rng = np.random.default_rng(23)
+    n, mx = 1_000_000, 40
+    A = designed_matrix(rng, np.float64, n, 16, 40)
+    v1 = rng.random(n)
+    ctx = b2a.default_context()
+    op = b2a.Operator.from_matrix(ctx, A)
+    ws = b2a.ArnoldiWorkspace(v1, mx, ctx=ctx)
+    ws.reinitialize(0, "keep")
+    st = ws.iterate_arnoldi(op, 1, mx)
+    assert st.matvecs == mx
+    V, H = ws.V, np.array(ws.H)
+    G = V.T @ V
+    assert np.abs(G - np.eye(mx + 1)).max() < 1e-13
+    R = A @ V[:, :mx] - V @ H
+    assert np.linalg.norm(R) < 1e-12 * np.linalg.norm(H)
+    assert np.all(np.tril(H[:mx, :], -2) == 0)

@@ -1,0 +1,221 @@
+"""C++ host driver (m x m algebra inside libb200arnoldi.so) against the oracle - CPU only.
+
+The product keeps the Hessenberg/Schur algebra on the host in C++; these tests call it
+through the C ABI's b2a_host_* entry points and compare with oracle/dense_small.py on
+identical inputs, then run complete partialschur problems with the oracle's expansion
+and the C++ restart step.
+"""
+
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import b200arnoldi as b2a
+import oracle
+from oracle import dense_small as ds
+from oracle import krylov_schur as ks
+
+EPS = np.finfo(np.float64).eps
+TYPES = [np.float64, np.complex128]
+WHICH = {"LM": 0, "LR": 1, "SR": 2, "LI": 3, "SI": 4}
+
+
+def code(T):
+    return 1 if T is np.complex128 else 0
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def cxx_restart(H, Q, maxdim, mindim, nev, tol, which, active):
+    lib = b2a.lib()
+    k, purge, nlock = C.c_int(), C.c_int(), C.c_int()
+    eig = np.zeros(2 * maxdim)
+    res = np.zeros(maxdim)
+    st = lib.b2a_host_restart(code(H.dtype.type), ptr(H), H.shape[0], ptr(Q), Q.shape[0], maxdim, mindim, nev,
+                              float(tol), WHICH[which], active, C.byref(k), C.byref(purge), C.byref(nlock),
+                              ptr(eig), ptr(res))
+    assert st == 0, lib.b2a_last_error()
+    return k.value, purge.value, nlock.value, eig.view(np.complex128), res
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_givens_matches_oracle(T):
+    rng = np.random.default_rng(0)
+    lib = b2a.lib()
+    for _ in range(200):
+        if T is np.complex128:
+            f, g = rng.standard_normal(2) + 1j * rng.standard_normal(2)
+        else:
+            f, g = rng.standard_normal(2)
+        if rng.random() < 0.1:
+            g = 0 * g
+        if rng.random() < 0.1:
+            f = 0 * f
+        fa, ga = np.array([f], dtype=T), np.array([g], dtype=T)
+        c = C.c_double()
+        s, r = np.zeros(1, dtype=T), np.zeros(1, dtype=T)
+        assert lib.b2a_host_givens(code(T), ptr(fa), ptr(ga), C.byref(c), ptr(s), ptr(r)) == 0
+        co, so, ro = oracle.givens_algorithm(T(f), T(g))
+        assert c.value == co and s[0] == so and r[0] == ro  # same algorithm, same rounding
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_local_schurfact_matches_oracle(T):
+    rng = np.random.default_rng(1)
+    lib = b2a.lib()
+    for n, lo, hi in [(10, 1, 10), (10, 3, 8), (20, 5, 20), (6, 1, 6)]:
+        H = np.triu(rng.standard_normal((n, n)), -1).astype(T)
+        if T is np.complex128:
+            H = H + 1j * np.triu(rng.standard_normal((n, n)), -1)
+        H = np.asfortranarray(H)
+        # outside the window the matrix must already be triangular
+        for j in range(n - 1):
+            if j + 1 < lo or j + 2 > hi:
+                H[j + 1, j] = 0
+        H1, Q1 = H.copy(order="F"), np.asfortranarray(np.eye(n, dtype=T))
+        H2, Q2 = H.copy(order="F"), np.asfortranarray(np.eye(n, dtype=T))
+        assert lib.b2a_host_local_schurfact(code(T), ptr(H1), n, n, n, lo, hi, ptr(Q1), n, n) == 0
+        assert ds.local_schurfact(H2, lo, hi, Q2)
+        assert np.linalg.norm(H @ Q1 - Q1 @ H1) < 1000 * EPS * np.linalg.norm(H)
+        assert np.allclose(H1, H2, rtol=0, atol=1e-12 * np.linalg.norm(H))
+        assert np.allclose(Q1, Q2, rtol=0, atol=1e-12)
+
+
+def arnoldi_state(rng, T, n, maxdim, A=None):
+    if A is None:
+        A = rng.standard_normal((n, n)).astype(T)
+        if T is np.complex128:
+            A = A + 1j * rng.standard_normal((n, n))
+    arn = oracle.ArnoldiWorkspace(T, n, maxdim)
+    oracle.reinitialize(arn, 0, rng=rng)
+    oracle.iterate_arnoldi(A, arn, 1, maxdim, rng=rng)
+    return A, arn
+
+
+@pytest.mark.parametrize("T", TYPES)
+@pytest.mark.parametrize("which", ["LM", "SR", "LR"])
+def test_restart_step_matches_oracle(T, which):
+    rng = np.random.default_rng(2)
+    n, maxdim, mindim, nev = 60, 20, 10, 6
+    A, arn = arnoldi_state(rng, T, n, maxdim)
+    H1, Q1 = arn.H.copy(order="F"), np.asfortranarray(np.zeros((maxdim, maxdim), dtype=T))
+    H2, Q2 = arn.H.copy(order="F"), np.asfortranarray(np.zeros((maxdim, maxdim), dtype=T))
+    k1, purge1, nlock1, lam1, rs1 = cxx_restart(H1, Q1, maxdim, mindim, nev, 1e-8, which, 1)
+    k2, purge2, nlock2, _, lam2, rs2 = ks.restart_decision(
+        H2, Q2, maxdim, mindim, nev, 1e-8, ds.Ordering(which), 1, T is np.float64
+    )
+    assert (k1, purge1, nlock1) == (k2, purge2, nlock2)
+    assert np.allclose(lam1, lam2, rtol=1e-10, atol=1e-12)
+    assert np.allclose(rs1, rs2, rtol=1e-6, atol=1e-12)
+    scale = np.linalg.norm(arn.H)
+    assert np.allclose(H1, H2, rtol=0, atol=1e-10 * scale)
+    assert np.allclose(Q1, Q2, rtol=0, atol=1e-10)
+    # and the truncated relation holds: A (V Q[:, :k]) = [V Q[:, :k], v_{m+1}] H[:k+1, :k]
+    W = np.hstack([arn.V[:, :maxdim] @ Q1[:, :k1], arn.V[:, maxdim : maxdim + 1]])
+    assert np.linalg.norm(A @ W[:, :k1] - W @ H1[: k1 + 1, :k1]) < 1e-10 * scale
+
+
+class CxxRestartSolver:
+    """Test-only composition: the oracle's n-sized expansion + the product's C++ restart step.
+    (The product itself never runs this on the CPU - its expansion is CUDA.)"""
+
+    @staticmethod
+    def solve(A, T, nev, which, tol, mindim, maxdim, restarts, rng, v1=None):
+        n = A.shape[0]
+        arn = oracle.ArnoldiWorkspace(T, n, maxdim)
+        if v1 is None:
+            oracle.reinitialize(arn, 0, rng=rng)
+        else:
+            arn.V[:, 0] = v1 / np.linalg.norm(v1)
+        H, V, Q = arn.H, arn.V, arn.Q
+        active, k = 1, mindim
+        prods = mindim
+        oracle.iterate_arnoldi(A, arn, 1, mindim, rng=rng)
+        for _ in range(restarts):
+            oracle.iterate_arnoldi(A, arn, k + 1, maxdim, rng=rng)
+            prods += maxdim - k
+            k, purge, nlock, _, _ = cxx_restart(H, Q, maxdim, mindim, nev, tol, which, active)
+            V[:, purge - 1 : k] = V[:, purge - 1 : maxdim] @ Q[purge - 1 : maxdim, purge - 1 : k]
+            V[:, k] = V[:, maxdim]
+            active = nlock + 1
+            if active > nev:
+                break
+        nconv = active - 1
+        st = b2a.lib().b2a_host_sortschur(code(T), ptr(H), H.shape[0], ptr(Q), Q.shape[0], maxdim, nconv, WHICH[which])
+        assert st == 0
+        V[:, :nconv] = V[:, :nconv] @ Q[:nconv, :nconv]
+        return V[:, :nconv].copy(), H[:nconv, :nconv].copy(), prods, nconv
+
+
+def test_cxx_driver_readme_example():
+    n = 100
+    A = sp.diags([-np.ones(n - 1), 2 * np.ones(n), -np.ones(n - 1)], [-1, 0, 1], format="csr")
+    exact = 2 - 2 * np.cos(np.arange(1, 11) * np.pi / 101)
+    for seed in range(3):
+        rng = np.random.default_rng(seed)
+        v1 = rng.random(n)
+        Qc, Rc, prods, nconv = CxxRestartSolver.solve(A, np.float64, 10, "SR", 1e-6, 10, 20, 200, rng, v1)
+        P, hist = oracle.partialschur(A, v1=v1, nev=10, tol=1e-6, which="SR", rng=np.random.default_rng(seed))
+        assert nconv == hist.nconverged == 10
+        assert prods == hist.mvproducts  # same decisions restart by restart
+        assert np.allclose(np.sort(np.diag(Rc)), exact, atol=1e-11)
+        assert np.linalg.norm(A @ Qc - Qc @ Rc) < 1e-6
+        assert np.allclose(np.abs(Qc.T @ P.Q), np.eye(10), atol=1e-6)
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_cxx_driver_exact_counts(T):
+    rng = np.random.default_rng(3)
+    B = rng.random((10, 3)) + (1j * rng.random((10, 3)) if T is np.complex128 else 0)
+    B = B @ B.conj().T
+    Qc, Rc, prods, nconv = CxxRestartSolver.solve(B, T, 5, "LM", EPS, 5, 7, 200, rng)
+    assert prods == 7 and nconv >= 5  # test/partial_schur.jl:22
+    assert np.linalg.norm(B @ Qc - Qc @ Rc) < 1000 * EPS
+    Z = np.zeros((5, 5), dtype=T)
+    Qc, Rc, prods, nconv = CxxRestartSolver.solve(Z, T, 5, "LM", np.sqrt(EPS), 5, 5, 200, rng)
+    assert prods == nconv == 5  # test/partial_schur.jl:116
+    assert np.linalg.norm(Z @ Qc - Qc @ Rc) == 0
+
+
+def test_cxx_driver_conjugate_pairs_real():
+    rng = np.random.default_rng(4)
+    A = rng.standard_normal((200, 200))
+    v1 = rng.random(200)
+    Qc, Rc, prods, nconv = CxxRestartSolver.solve(A, np.float64, 8, "LM", 1e-8, 10, 20, 400, rng, v1)
+    P, hist = oracle.partialschur(A, v1=v1, nev=8, tol=1e-8, which="LM", rng=np.random.default_rng(4), restarts=400)
+    assert nconv == hist.nconverged and nconv in (8, 9)
+    assert abs(prods - hist.mvproducts) <= 10  # within one restart's worth (SURVEY 8(c) iv)
+    assert np.linalg.norm(A @ Qc - Qc @ Rc) < 200 * 1e-8 * np.abs(np.linalg.eigvals(Rc)).max()
+    assert np.allclose(np.sort_complex(np.linalg.eigvals(Rc)), np.sort_complex(P.eigenvalues), atol=1e-7)
+
+
+@pytest.mark.parametrize("which", ["LM", "LR", "SR", "LI", "SI"])
+def test_cxx_driver_complex_targets(which):
+    rng = np.random.default_rng(5)
+    n = 60
+    d = rng.standard_normal(n) * 10 + 10j * rng.standard_normal(n)
+    A = np.diag(d) + 0.01 * (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n)))
+    Qc, Rc, prods, nconv = CxxRestartSolver.solve(A, np.complex128, 4, which, 1e-9, 10, 20, 500, rng)
+    assert nconv >= 4
+    ev = np.linalg.eigvals(A)
+    key = {"LM": -abs(ev), "LR": -ev.real, "SR": ev.real, "LI": -ev.imag, "SI": ev.imag}[which]
+    got = np.diag(Rc)
+    for w in ev[np.argsort(key)[:4]]:
+        assert abs(got - w).min() < 1e-6
+    # sortschur put them in the wanted order
+    k2 = {"LM": -abs(got), "LR": -got.real, "SR": got.real, "LI": -got.imag, "SI": got.imag}[which]
+    assert np.all(np.diff(k2) >= -1e-9)
+
+
+def test_host_argument_errors():
+    lib = b2a.lib()
+    H = np.zeros((5, 4), order="F")
+    Q = np.zeros((4, 4), order="F")
+    k = C.c_int()
+    assert lib.b2a_host_restart(0, ptr(H), 5, ptr(Q), 4, 4, 2, 3, 1e-8, 0, 1, C.byref(k), None, None, None, None) == -1
+    assert lib.b2a_host_restart(0, ptr(H), 5, ptr(Q), 4, 4, 2, 2, 1e-8, 7, 1, C.byref(k), None, None, None, None) == -1
+    assert b"Unknown target" in lib.b2a_last_error()
