@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libb200arnoldi.so")
 F64, C64 = 0, 1
 WHICH = {"LM": 0, "LR": 1, "SR": 2, "LI": 3, "SI": 4}
 INIT_NONE, INIT_RAND, INIT_KEEP = 0, 1, 2
+KERNEL_KINDS = ("spmv", "cgs_dots", "cgs_update", "cgs_finish", "rotate", "fill")
 OK, ERR_ARGUMENT, ERR_DIMENSION, ERR_CUDA, ERR_NCCL, ERR_OOM, ERR_QR, ERR_INTERNAL, ERR_CALLBACK = (
     0, -1, -2, -3, -4, -5, -6, -7, -8,
 )
@@ -76,6 +77,8 @@ SIGNATURES = {
     "b2a_ctx_sync": (_i, [_vp]),
     "b2a_ctx_rank": (_i, [_vp, _pi, _pi]),
     "b2a_ctx_launch_count": (_i, [_vp, _pi64]),
+    "b2a_ctx_profile_enable": (_i, [_vp, _i]),
+    "b2a_ctx_profile_get": (_i, [_vp, _i, _pi64, _pd, _pd]),
     "b2a_csr_create": (_i, [_vp, _i, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _i, _i, _pvp]),
     "b2a_csr_create_device": (_i, [_vp, _i, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _pvp]),
     "b2a_csc_create": (_i, [_vp, _i, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _pvp]),

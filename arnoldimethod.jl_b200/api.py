@@ -88,6 +88,19 @@ class Context:
         L.check(L.lib().b2a_ctx_launch_count(self._h, C.byref(v)))
         return v.value
 
+    def profile(self, on=True):
+        """Enable / disable (and reset) per-kernel-kind CUDA-event timing."""
+        L.check(L.lib().b2a_ctx_profile_enable(self._h, 1 if on else 0))
+
+    def profile_report(self):
+        """-> {kind: dict(launches, ms, bytes)} accumulated since ``profile(True)``."""
+        out = {}
+        for k, name in enumerate(L.KERNEL_KINDS):
+            n, ms, by = C.c_int64(), C.c_double(), C.c_double()
+            L.check(L.lib().b2a_ctx_profile_get(self._h, k, C.byref(n), C.byref(ms), C.byref(by)))
+            out[name] = dict(launches=n.value, ms=ms.value, bytes=by.value)
+        return out
+
     def close(self):
         if self._h:
             L.lib().b2a_ctx_destroy(self._h)
@@ -296,9 +309,14 @@ class ArnoldiWorkspace:
             raise ValueError("v1 should have the same dimension as A")  # src/run.jl:123-124
         L.check(L.lib().b2a_ws_set_col(self._h, int(j), _ptr(vec)))
 
-    def get_cols(self, j0, ncols):
-        """Host copy of ``V[:, j0:j0+ncols-1]`` (1-based), column-major."""
-        out = np.zeros((self.n_local, ncols), dtype=self.dtype, order="F")
+    def get_cols(self, j0, ncols, out=None):
+        """Host copy of ``V[:, j0:j0+ncols-1]`` (1-based), column-major.  ``out``: optional
+        (e.g. pinned) Fortran-ordered destination with at least ``ncols`` columns."""
+        if out is None:
+            out = np.zeros((self.n_local, ncols), dtype=self.dtype, order="F")
+        else:
+            assert out.dtype == self.dtype and out.flags.f_contiguous and out.shape[0] == self.n_local
+            out = out[:, :ncols]
         if ncols > 0 and self.n_local > 0:
             L.check(L.lib().b2a_ws_get_cols(self._h, int(j0), int(ncols), _ptr(out), max(self.n_local, 1)))
         return out

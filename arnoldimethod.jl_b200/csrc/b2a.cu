@@ -118,7 +118,65 @@ struct b2a_ctx {
   int64_t launches = 0;
   int num_sms = b2a::kSMs;
   int *d_zero = nullptr;  // a device int that is always 0 (poison stand-in outside sweeps)
+  // optional per-kernel-kind timing (b2a_ctx_profile_*)
+  struct ProfRec {
+    int kind;
+    double bytes;
+    int gate_step;  // > 0: launch belongs to the gated second pass of that step
+    cudaEvent_t e0, e1;
+  };
+  bool prof_on = false;
+  std::vector<ProfRec> prof_pending;
+  std::vector<cudaEvent_t> prof_pool;
+  int64_t prof_n[B2A_K_COUNT] = {0};
+  double prof_ms[B2A_K_COUNT] = {0}, prof_bytes[B2A_K_COUNT] = {0};
 };
+
+static cudaEvent_t prof_event(b2a_ctx *c) {
+  cudaEvent_t e;
+  if (!c->prof_pool.empty()) {
+    e = c->prof_pool.back();
+    c->prof_pool.pop_back();
+  } else {
+    cudaEventCreate(&e);
+  }
+  return e;
+}
+static inline void prof_begin(b2a_ctx *c, int kind, double bytes, int gate_step = 0) {
+  if (!c->prof_on) return;
+  b2a_ctx::ProfRec r{kind, bytes, gate_step, prof_event(c), prof_event(c)};
+  cudaEventRecord(r.e0, c->stream);
+  c->prof_pending.push_back(r);
+}
+static inline void prof_end(b2a_ctx *c) {
+  if (!c->prof_on) return;
+  cudaEventRecord(c->prof_pending.back().e1, c->stream);
+}
+// call after a stream synchronisation; info[step - info_base] bit0 tells whether the gated
+// second pass of `step` really ran (gated-off launches are dropped from the statistics)
+static void prof_collect(b2a_ctx *c, const int *info, int info_base, int info_count) {
+  if (!c->prof_on) return;
+  for (auto &r : c->prof_pending) {
+    bool executed = true;
+    if (r.gate_step > 0) {
+      const int i = r.gate_step - info_base;
+      executed = info && i >= 0 && i < info_count && (info[i] & 1);
+    }
+    if (executed) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+        c->prof_n[r.kind] += 1;
+        c->prof_ms[r.kind] += ms;
+        c->prof_bytes[r.kind] += r.bytes;
+      } else {
+        (void)cudaGetLastError();
+      }
+    }
+    c->prof_pool.push_back(r.e0);
+    c->prof_pool.push_back(r.e1);
+  }
+  c->prof_pending.clear();
+}
 
 enum OpKind { OP_CSR = 0, OP_CSC_SCATTER = 1, OP_CALLBACK = 2 };
 
@@ -187,16 +245,18 @@ static int allreduce_f64(b2a_ctx *ctx, void *buf, size_t count) {
 // ---- Gram-Schmidt launches ------------------------------------------------------
 template <class DT, int CPW, int U>
 static int launch_dots_inst(b2a_ws *ws, const DT *V, const DT *v, int ncols, DT *hout, double *nrm2,
-                            const double *g_rsq, const double *g_w1sq) {
+                            const double *g_rsq, const double *g_w1sq, int gate_step) {
   constexpr int PV = b2a::Scalar<DT>::per_vec;
   const int64_t n = ws->n_local;
   const int64_t quantum = 32 * PV * U;
   int64_t grid = std::max<int64_t>(1, std::min<int64_t>(ws->dots_grid_max, cdiv(n, quantum)));
   const int64_t rows_per_cta = round_up(cdiv(n, grid), quantum);
   grid = std::max<int64_t>(1, cdiv(n, rows_per_cta));
+  prof_begin(ws->ctx, B2A_K_DOTS, (double)(ncols + 1) * n * sizeof(DT), gate_step);
   b2a::cgs_dots_kernel<DT, CPW, U><<<(unsigned)grid, b2a::kCgsThreads, 0, ws->ctx->stream>>>(
       V, ws->ld, v, n, ncols, rows_per_cta, reinterpret_cast<DT *>(ws->partials), hout, nrm2,
       &ws->state->ticket[0], &ws->state->poison, g_rsq, g_w1sq);
+  prof_end(ws->ctx);
   ws->ctx->launches++;
   CUDA_TRY(cudaGetLastError());
   return B2A_OK;
@@ -205,7 +265,7 @@ static int launch_dots_inst(b2a_ws *ws, const DT *V, const DT *v, int ncols, DT 
 // dots over panel columns [0, ncols) in blocks of at most 64 columns
 template <class DT>
 static int launch_dots(b2a_ws *ws, int ncols, const DT *v, DT *hout, double *nrm2, const double *g_rsq,
-                       const double *g_w1sq) {
+                       const double *g_w1sq, int gate_step = 0) {
   const DT *V = col<DT>(ws, 0);
   int done = 0;
   bool first = true;
@@ -217,14 +277,14 @@ static int launch_dots(b2a_ws *ws, int ncols, const DT *v, DT *hout, double *nrm
     DT *hb = hout + done;
     int s;
     switch (cpw) {
-      case 1: s = launch_dots_inst<DT, 1, 8>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq); break;
-      case 2: s = launch_dots_inst<DT, 2, 8>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq); break;
-      case 3: s = launch_dots_inst<DT, 3, 4>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq); break;
-      case 4: s = launch_dots_inst<DT, 4, 4>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq); break;
-      case 5: s = launch_dots_inst<DT, 5, 2>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq); break;
-      case 6: s = launch_dots_inst<DT, 6, 2>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq); break;
-      case 7: s = launch_dots_inst<DT, 7, 2>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq); break;
-      default: s = launch_dots_inst<DT, 8, 2>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq); break;
+      case 1: s = launch_dots_inst<DT, 1, 8>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq, gate_step); break;
+      case 2: s = launch_dots_inst<DT, 2, 8>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq, gate_step); break;
+      case 3: s = launch_dots_inst<DT, 3, 4>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq, gate_step); break;
+      case 4: s = launch_dots_inst<DT, 4, 4>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq, gate_step); break;
+      case 5: s = launch_dots_inst<DT, 5, 2>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq, gate_step); break;
+      case 6: s = launch_dots_inst<DT, 6, 2>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq, gate_step); break;
+      case 7: s = launch_dots_inst<DT, 7, 2>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq, gate_step); break;
+      default: s = launch_dots_inst<DT, 8, 2>(ws, Vb, v, nc, hb, nrm, g_rsq, g_w1sq, gate_step); break;
     }
     B2A_TRY(s);
     done += nc;
@@ -235,13 +295,15 @@ static int launch_dots(b2a_ws *ws, int ncols, const DT *v, DT *hout, double *nrm
 
 template <class DT>
 static int launch_update(b2a_ws *ws, int ncols, DT *v, const DT *h, double *nrm2, const double *g_rsq,
-                         const double *g_w1sq) {
+                         const double *g_w1sq, int gate_step = 0) {
   constexpr int PV = b2a::Scalar<DT>::per_vec;
   const int64_t nvec = cdiv(ws->n_local, PV);
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(ws->upd_grid_max, cdiv(nvec, b2a::kCgsThreads)));
+  prof_begin(ws->ctx, B2A_K_UPDATE, (double)(ncols + 2) * ws->n_local * sizeof(DT), gate_step);
   b2a::cgs_update_kernel<DT><<<(unsigned)grid, b2a::kCgsThreads, ncols * sizeof(DT), ws->ctx->stream>>>(
       col<DT>(ws, 0), ws->ld, v, ws->n_local, ncols, h, ws->partials2, nrm2, &ws->state->ticket[1],
       &ws->state->poison, g_rsq, g_w1sq);
+  prof_end(ws->ctx);
   ws->ctx->launches++;
   CUDA_TRY(cudaGetLastError());
   return B2A_OK;
@@ -269,23 +331,27 @@ template <class DT> static int enqueue_cgs(b2a_ws *ws, int j, int mode, int step
     B2A_TRY(launch_update<DT>(ws, j, v, h1, w1sq, nullptr, nullptr));
     B2A_TRY(allreduce_f64(ctx, w1sq, 1));
     // pass 2, gated on the device by wnorm < eta * rnorm      (expansion.jl:91-96)
-    B2A_TRY(launch_dots<DT>(ws, j, v, h2, nullptr, rsq, w1sq));
+    B2A_TRY(launch_dots<DT>(ws, j, v, h2, nullptr, rsq, w1sq, j));
     B2A_TRY(allreduce_f64(ctx, h2, hd));
-    B2A_TRY(launch_update<DT>(ws, j, v, h2, ws->w2sq, rsq, w1sq));
+    B2A_TRY(launch_update<DT>(ws, j, v, h2, ws->w2sq, rsq, w1sq, j));
     B2A_TRY(allreduce_f64(ctx, ws->w2sq, 1));
   }
   constexpr int PV = b2a::Scalar<DT>::per_vec;
   const int64_t nvec = cdiv(ws->n_local, PV);
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(ws->upd_grid_max, cdiv(nvec, 256)));
   DT *Hcol = reinterpret_cast<DT *>(ws->dH) + (int64_t)(std::max(j, 1) - 1) * (ws->maxdim + 1);
+  prof_begin(ctx, B2A_K_FINISH, 2.0 * ws->n_local * sizeof(DT));
   b2a::cgs_finish_kernel<DT><<<(unsigned)grid, 256, 0, ctx->stream>>>(
       v, ws->n_local, j, h1, h2, rsq, w1sq, ws->w2sq, Hcol, ws->dinfo + j, ws->state, step, mode);
+  prof_end(ctx);
   ctx->launches++;
   CUDA_TRY(cudaGetLastError());
   return B2A_OK;
 }
 
 // ---- operator -------------------------------------------------------------------
+static double op_bytes(const b2a_op *A);
+
 template <class DT, int LPR>
 static void launch_spmv_vec(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms) {
   constexpr int U = 4;
@@ -331,6 +397,7 @@ template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, 
     }
     x = xf;
   }
+  prof_begin(ctx, B2A_K_SPMV, op_bytes(A));
   if (A->kind == OP_CSC_SCATTER) {
     b2a::zero_vector_kernel<DT><<<(unsigned)std::min<int64_t>(ctx->num_sms * 8, std::max<int64_t>(1, cdiv(A->n_local, 256))), 256, 0, ctx->stream>>>(y, A->n_local, poison);
     ctx->launches++;
@@ -357,6 +424,7 @@ template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, 
       default: launch_spmv_vec<DT, 32>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
     }
   }
+  prof_end(ctx);
   ctx->launches++;
   CUDA_TRY(cudaGetLastError());
   return B2A_OK;
@@ -374,8 +442,10 @@ static bool try_rotate(b2a_ws *ws, int col0, int K, int N, int move_src, int mov
     return false;
   }
   const int64_t grid = std::max<int64_t>(1, cdiv(ws->n_local, R));
+  prof_begin(ws->ctx, B2A_K_ROTATE, (double)ws->n_local * sizeof(DT) * (K + N + (move_dst >= 0 ? 2.0 : 0.0)));
   kern<<<(unsigned)grid, 256, smem, ws->ctx->stream>>>(reinterpret_cast<DT *>(ws->dV), ws->ld, ws->n_local, col0, K,
                                                          N, reinterpret_cast<const DT *>(ws->dQ), move_src, move_dst);
+  prof_end(ws->ctx);
   ws->ctx->launches++;
   return true;
 }
@@ -394,6 +464,7 @@ static int rotate(b2a_ws *ws, int col0, int K, int N, const HT *Qp, int move_src
   CUDA_TRY(cudaGetLastError());
   // Qp is a host temporary of the caller: make sure the copy has been consumed
   CUDA_TRY(cudaStreamSynchronize(ws->ctx->stream));
+  prof_collect(ws->ctx, nullptr, 0, 0);
   return B2A_OK;
 }
 
@@ -415,8 +486,10 @@ static uint64_t reseed_key(uint64_t seed, uint64_t counter) {
 
 template <class DT> static int enqueue_fill(b2a_ws *ws, int j0, uint64_t key) {
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)ws->ctx->num_sms * 8, cdiv(ws->n_local, 256)));
+  prof_begin(ws->ctx, B2A_K_FILL, (double)ws->n_local * sizeof(DT));
   b2a::fill_uniform_kernel<DT><<<(unsigned)grid, 256, 0, ws->ctx->stream>>>(col<DT>(ws, j0), ws->n_local,
                                                                             ws->row_offset, key, ws->ctx->d_zero);
+  prof_end(ws->ctx);
   ws->ctx->launches++;
   CUDA_TRY(cudaGetLastError());
   return B2A_OK;
@@ -438,6 +511,7 @@ template <class HT> static int reinitialize(b2a_ws *ws, int j, int mode, uint64_
   CUDA_TRY(cudaMemcpyAsync(ws->pinned, ws->dinfo + j, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   std::memcpy(&info, ws->pinned, sizeof(int));
+  prof_collect(ctx, &info, j, 1);
   if (ok) *ok = (j == 0) ? 1 : ((info & 2) ? 0 : 1);
   if (st) {
     const int passes = (j == 0) ? 0 : ((info & 1) ? 2 : 1);
@@ -475,6 +549,7 @@ static int iterate_arnoldi(b2a_ws *ws, b2a_op *A, int from, int to, uint64_t see
     b2a::SweepState state;
     std::memcpy(&state, p + hbytes + ncols * sizeof(int), sizeof(state));
     const int *info = reinterpret_cast<const int *>(p + hbytes);
+    prof_collect(ctx, info, j, ncols);
     const int last = state.poison ? state.poison : to;  // last step that really executed
     const HT *Hn = reinterpret_cast<const HT *>(p);
     for (int s = j; s <= last; ++s) {
@@ -689,6 +764,11 @@ int b2a_ctx_create_dist(int device, int rank, int world, const void *nccl_unique
 int b2a_ctx_destroy(b2a_ctx *ctx) {
   if (!ctx) return B2A_OK;
   cudaSetDevice(ctx->device);
+  for (auto &r : ctx->prof_pending) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  for (auto e : ctx->prof_pool) cudaEventDestroy(e);
   if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
   if (ctx->d_zero) cudaFree(ctx->d_zero);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -715,6 +795,25 @@ int b2a_ctx_rank(b2a_ctx *ctx, int *rank, int *world) {
 int b2a_ctx_launch_count(b2a_ctx *ctx, int64_t *launches) {
   if (!ctx || !launches) return fail(B2A_ERR_ARGUMENT, "NULL argument");
   *launches = ctx->launches;
+  return B2A_OK;
+}
+
+int b2a_ctx_profile_enable(b2a_ctx *ctx, int on) {
+  if (!ctx) return fail(B2A_ERR_ARGUMENT, "NULL ctx");
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  prof_collect(ctx, nullptr, 0, 0);
+  ctx->prof_on = on != 0;
+  for (int k = 0; k < B2A_K_COUNT; ++k) {
+    ctx->prof_n[k] = 0;
+    ctx->prof_ms[k] = ctx->prof_bytes[k] = 0.0;
+  }
+  return B2A_OK;
+}
+int b2a_ctx_profile_get(b2a_ctx *ctx, int kind, int64_t *launches, double *ms, double *bytes) {
+  if (!ctx || kind < 0 || kind >= B2A_K_COUNT) return fail(B2A_ERR_ARGUMENT, "bad kernel kind");
+  if (launches) *launches = ctx->prof_n[kind];
+  if (ms) *ms = ctx->prof_ms[kind];
+  if (bytes) *bytes = ctx->prof_bytes[kind];
   return B2A_OK;
 }
 
@@ -910,13 +1009,13 @@ int b2a_csc_create(b2a_ctx *ctx, int dtype, int64_t n_global, int64_t nnz, const
   }
   for (int64_t r = 0; r < n_global; ++r) rowptr[(size_t)r + 1] += rowptr[(size_t)r];
   std::vector<int64_t> fill(rowptr.begin(), rowptr.end() - 1);
-  std::vector<int32_t> colind((size_t)nnz);
+  std::vector<int64_t> colind((size_t)nnz);
   std::vector<char> vals((size_t)nnz * es);
   for (int64_t c = 0; c < n_global; ++c) {
     const int64_t s = cptr(c), e = cptr(c + 1);
     for (int64_t i = s; i < e; ++i) {
       const int64_t dst = fill[(size_t)ridx(i)]++;
-      colind[(size_t)dst] = (int32_t)c;
+      colind[(size_t)dst] = c;
       std::memcpy(&vals[(size_t)dst * es], reinterpret_cast<const char *>(nzval) + (size_t)i * es, es);
     }
   }
@@ -1118,6 +1217,7 @@ template <class HT> static int orthogonalize_impl(b2a_ws *ws, int j, void *h_hos
   if (h_host) std::memcpy(h_host, ws->pinned, (size_t)(j + 1) * sizeof(HT));
   int info;
   std::memcpy(&info, ws->pinned + (size_t)m1 * sizeof(HT), sizeof(int));
+  prof_collect(ws->ctx, &info, j, 1);
   if (ok) *ok = (info & 2) ? 0 : 1;
   return B2A_OK;
 }

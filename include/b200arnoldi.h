@@ -86,6 +86,21 @@ int b2a_ctx_rank(b2a_ctx *ctx, int *rank, int *world);
 /* number of this library's kernels launched on the context so far */
 int b2a_ctx_launch_count(b2a_ctx *ctx, int64_t *launches);
 
+/* Per-kernel-kind device timing (CUDA events on the context's stream around every launch of
+ * this library's kernels).  Off by default; meant for benchmarks: kernel durations are
+ * accumulated at the library's own synchronisation points (end of a sweep / rotation). */
+enum b2a_kernel_kind {
+  B2A_K_SPMV = 0,   /* operator mat-vec                                                  */
+  B2A_K_DOTS = 1,   /* cgs_dots   (h = V' v, ||v||^2)        bytes/launch = (j+1) n s    */
+  B2A_K_UPDATE = 2, /* cgs_update (v -= V h, ||v||^2)        bytes/launch = (j+2) n s    */
+  B2A_K_FINISH = 3, /* cgs_finish (H column, v ./= wnorm)    bytes/launch = 2 n s        */
+  B2A_K_ROTATE = 4, /* in-place V <- V Q                                                 */
+  B2A_K_FILL = 5,   /* counter-based rand!                                               */
+  B2A_K_COUNT = 6
+};
+int b2a_ctx_profile_enable(b2a_ctx *ctx, int on); /* also resets the accumulators */
+int b2a_ctx_profile_get(b2a_ctx *ctx, int kind, int64_t *launches, double *ms, double *bytes);
+
 /* --------------------------------------------------------------------- operator
  * Replaces the user operator of `mul!(y, A, x)`, `eltype(A)`, `size(A)`
  * (contract: src/run.jl:21-25; call site: src/expansion.jl:121).               */

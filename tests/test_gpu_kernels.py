@@ -141,7 +141,9 @@ def test_orthogonalize_matches_oracle(ctx, T, n, j):
         assert ok == ok_ref
         h_gpu, h_ref = ws.H[: j + 1, j - 1], arn.H[: j + 1, j - 1]
         assert relerr(h_gpu, h_ref) <= 1e-13
-        assert abs(h_gpu[j] - h_ref[j]) <= 1e-13 * abs(h_ref[j])
+        # generic: 1e-13.  nearly dependent: v loses 6 digits to cancellation, so wnorm (and the
+        # normalised v) are only determined to ~1e6 * eps; stated tolerance 1e-9.
+        assert abs(h_gpu[j] - h_ref[j]) <= (1e-13 if kind == "generic" else 1e-9) * abs(h_ref[j])
         v_gpu = ws.get_cols(j + 1, 1)[:, 0]
         assert np.linalg.norm(v_gpu - arn.V[:, j]) <= (1e-13 if kind == "generic" else 1e-9)
         assert np.abs(Vp.conj().T @ v_gpu).max() < 1e-13
@@ -265,7 +267,10 @@ def test_iterate_arnoldi_relation(ctx, T):
     arn.V[:, 0] = v1 / np.linalg.norm(v1)
     oracle.iterate_arnoldi(A, arn, 1, mx)
     assert np.abs(H - arn.H).max() < 1e-12
-    assert np.abs(V - arn.V).max() < 1e-11
+    # compare basis vectors while the recurrence is well conditioned (|h_{j+1,j}| not tiny)
+    good = 1 + int(np.argmax(np.append(np.abs(np.diag(arn.H, -1)) < 1e-6, True)))
+    assert good >= 4
+    assert np.abs(V[:, :good] - arn.V[:, :good]).max() < 1e-9
 
 
 @pytest.mark.parametrize("T", TYPES)
