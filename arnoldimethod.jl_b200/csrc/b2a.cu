@@ -21,6 +21,7 @@
 #include <chrono>
 #include <complex>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -29,6 +30,7 @@
 #include "device_common.cuh"
 #include "host_dense.hpp"
 #include "kernels_cgs.cuh"
+#include "kernels_cgs_tma.cuh"
 #include "kernels_rotate.cuh"
 #include "kernels_spmv.cuh"
 
@@ -130,7 +132,37 @@ struct b2a_ctx {
   std::vector<cudaEvent_t> prof_pool;
   int64_t prof_n[B2A_K_COUNT] = {0};
   double prof_ms[B2A_K_COUNT] = {0}, prof_bytes[B2A_K_COUNT] = {0};
+  // pinned host staging buffers are expensive to create: recycled across workspaces
+  std::vector<std::pair<size_t, char *>> pinned_cache;
 };
+
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync) with an unlimited
+// release threshold: after the first solve, creating and destroying operators / workspaces costs
+// microseconds instead of the milliseconds of cudaMalloc / cudaFree (which also synchronise).
+static cudaError_t dev_alloc(b2a_ctx *c, void **p, size_t bytes) {
+  return cudaMallocAsync(p, std::max<size_t>(bytes, 16), c->stream);
+}
+static void dev_free(b2a_ctx *c, void *p) {
+  if (p) cudaFreeAsync(p, c->stream);
+}
+static cudaError_t pinned_get(b2a_ctx *c, size_t bytes, char **out, size_t *got) {
+  for (size_t i = 0; i < c->pinned_cache.size(); ++i)
+    if (c->pinned_cache[i].first >= bytes) {
+      *out = c->pinned_cache[i].second;
+      *got = c->pinned_cache[i].first;
+      c->pinned_cache.erase(c->pinned_cache.begin() + i);
+      return cudaSuccess;
+    }
+  *got = bytes;
+  return cudaMallocHost(reinterpret_cast<void **>(out), bytes);
+}
+static void pinned_put(b2a_ctx *c, char *p, size_t bytes) {
+  if (!p) return;
+  if (c->pinned_cache.size() < 8)
+    c->pinned_cache.emplace_back(bytes, p);
+  else
+    cudaFreeHost(p);
+}
 
 static cudaEvent_t prof_event(b2a_ctx *c) {
   cudaEvent_t e;
@@ -190,6 +222,7 @@ struct b2a_op {
   void *d_vals = nullptr;
   bool owns = true;
   int lpr = 8;  // lanes per row (column)
+  int rows_in_flight = 4, grid_mult = 8;  // SpMV tuning (env B2A_SPMV_U / B2A_SPMV_GRID)
   b2a_matvec_fn fn = nullptr;
   void *user = nullptr;
 };
@@ -201,6 +234,7 @@ struct b2a_ws {
   int maxdim = 0;
   size_t esz = 8;
   void *dV = nullptr;  // ld x (maxdim+1)
+  void *arena = nullptr;  // one allocation behind all the small device scratch arrays below
   std::vector<char> H, Q;  // host, column-major: (maxdim+1) x maxdim and maxdim x maxdim
   // device scratch
   void *dH = nullptr;        // (maxdim+1) x maxdim, filled column by column by cgs_finish
@@ -219,6 +253,8 @@ struct b2a_ws {
   uint64_t reseed_counter = 0;
   std::vector<int64_t> all_offsets, all_counts;  // row partition over ranks
   bool uniform_partition = true;
+  bool use_tma = true;  // TMA-pipelined Gram-Schmidt sweeps (B2A_NO_TMA=1 selects the LDG kernels)
+  int tune_rt_dots = 0, tune_rt_upd = 0, tune_stages = 0, tune_grid_mult = 1;  // experiment overrides (env)
 };
 
 template <class HT> struct Dev;
@@ -309,6 +345,182 @@ static int launch_update(b2a_ws *ws, int ncols, DT *v, const DT *h, double *nrm2
   return B2A_OK;
 }
 
+
+// ---- TMA-pipelined Gram-Schmidt sweeps (kernels_cgs_tma.cuh) ---------------------------
+static constexpr size_t kTmaSmemBudget = 220 * 1024;
+
+// cuTensorMapEncodeTiled comes from the driver; resolve it through the runtime so that the
+// library has no link-time dependency on libcuda (it must load on GPU-less hosts).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+// Tensor map over columns [0, ncols] of V (panel + the column being orthogonalised), box = one tile.
+static bool make_panel_tmap(const b2a_ws *ws, int ncols, int RT, CUtensorMap *tm) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t inner = ws->esz / 8;  // ComplexF64 = 2 doubles per row
+  if ((cuuint64_t)RT * inner > 256 || ncols + 1 > 256) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)ws->ld * inner, (cuuint64_t)(ncols + 1)};
+  cuuint64_t gstride[1] = {(cuuint64_t)ws->ld * ws->esz};
+  cuuint32_t box[2] = {(cuuint32_t)(RT * inner), (cuuint32_t)(ncols + 1)};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, ws->dV, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+         CUDA_SUCCESS;
+}
+
+// ring geometry for a sweep over (ncols + 1) columns of `elem`-byte elements
+static bool tma_geometry(const b2a_ws *ws, int ncols, size_t elem, bool update, bool reverse, b2a::TmaGeom *g,
+                         size_t *smem_bytes, int *grid) {
+  if (ncols > b2a::kTmaMaxCols) return false;
+  const size_t header = 256 + (update ? b2a::kTmaMaxCols * elem : 0);
+  const size_t row_bytes = (size_t)(ncols + 1) * elem;
+  const int min_rt = elem == 8 ? 64 : 32;
+  const int max_rt = elem == 8 ? 256 : 128;  // tensor-map box: inner dimension <= 256 doubles
+  // rows per tile: ~64 KB stages (update: >= 256 rows when two such stages fit, so that all eight
+  // consumer warps own a 32-row slab in phase 1); never more rows than the vector has
+  int RT = max_rt;
+  while (RT > min_rt && (size_t)RT * row_bytes > 64 * 1024) RT >>= 1;
+  if (update && RT < 256 && max_rt >= 256 && 2 * 256 * row_bytes + header <= kTmaSmemBudget) RT = 256;
+  const int forced = update ? ws->tune_rt_upd : ws->tune_rt_dots;
+  if (forced >= min_rt && forced <= max_rt && (forced & (forced - 1)) == 0) RT = forced;
+  while (RT > min_rt && (int64_t)RT / 2 >= ws->n_local) RT >>= 1;
+  const size_t stage_bytes = (size_t)RT * row_bytes;
+  int stages = (int)std::min<size_t>(b2a::kTmaMaxStages, (kTmaSmemBudget - header) / stage_bytes);
+  if (ws->tune_stages >= 2) stages = std::min(stages, ws->tune_stages);
+  if (stages < 2) return false;
+  const int64_t ntiles = cdiv(std::max<int64_t>(ws->n_local, 1), RT);
+  if (ntiles > 2000000000LL) return false;
+  int gr = (int)std::min<int64_t>(ws->ctx->num_sms, ntiles);
+  const int tpc = (int)cdiv(ntiles, gr);
+  gr = (int)cdiv(ntiles, tpc);
+  stages = std::min(stages, std::max(2, tpc));
+  g->RT = RT;
+  g->stages = stages;
+  g->tiles_per_cta = tpc;
+  g->ntiles = (int)ntiles;
+  g->reverse = reverse ? 1 : 0;
+  *smem_bytes = header + (size_t)stages * stage_bytes;
+  *grid = gr;
+  return true;
+}
+
+template <class K> static int set_smem_attr(K kern, size_t smem) {
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBudget));
+  (void)smem;
+  return B2A_OK;
+}
+
+template <class DT, int CPW>
+static int launch_dots_tma_inst(b2a_ws *ws, const DT *v, int ncols, const b2a::TmaGeom &g, size_t smem, int grid,
+                                DT *hout, double *nrm2, const double *g_rsq, const double *g_w1sq, int gate_step) {
+  auto kern = b2a::cgs_dots_tma_kernel<DT, CPW>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    B2A_TRY(set_smem_attr(kern, smem));
+    attr_done = true;
+  }
+  CUtensorMap tm;
+  if (!make_panel_tmap(ws, ncols, g.RT, &tm)) return fail(B2A_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  (void)v;  // v is column `ncols` of the tensor map
+  prof_begin(ws->ctx, B2A_K_DOTS, (double)(ncols + 1) * ws->n_local * sizeof(DT), gate_step);
+  kern<<<grid, b2a::kTmaThreads, smem, ws->ctx->stream>>>(tm, ncols, g, reinterpret_cast<DT *>(ws->partials), hout,
+                                                            nrm2, &ws->state->ticket[2], &ws->state->poison, g_rsq,
+                                                            g_w1sq);
+  prof_end(ws->ctx);
+  ws->ctx->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return B2A_OK;
+}
+
+template <class DT>
+static int launch_dots_tma(b2a_ws *ws, int ncols, const DT *v, DT *hout, double *nrm2, const double *g_rsq,
+                           const double *g_w1sq, int gate_step, bool reverse) {
+  b2a::TmaGeom g;
+  size_t smem;
+  int grid;
+  if (!tma_geometry(ws, ncols, sizeof(DT), false, reverse, &g, &smem, &grid)) return 1;  // caller falls back
+  switch (std::max(1, (ncols + 7) / 8)) {
+    case 1: return launch_dots_tma_inst<DT, 1>(ws, v, ncols, g, smem, grid, hout, nrm2, g_rsq, g_w1sq, gate_step);
+    case 2: return launch_dots_tma_inst<DT, 2>(ws, v, ncols, g, smem, grid, hout, nrm2, g_rsq, g_w1sq, gate_step);
+    case 3: return launch_dots_tma_inst<DT, 3>(ws, v, ncols, g, smem, grid, hout, nrm2, g_rsq, g_w1sq, gate_step);
+    case 4: return launch_dots_tma_inst<DT, 4>(ws, v, ncols, g, smem, grid, hout, nrm2, g_rsq, g_w1sq, gate_step);
+    case 5: return launch_dots_tma_inst<DT, 5>(ws, v, ncols, g, smem, grid, hout, nrm2, g_rsq, g_w1sq, gate_step);
+    case 6: return launch_dots_tma_inst<DT, 6>(ws, v, ncols, g, smem, grid, hout, nrm2, g_rsq, g_w1sq, gate_step);
+    case 7: return launch_dots_tma_inst<DT, 7>(ws, v, ncols, g, smem, grid, hout, nrm2, g_rsq, g_w1sq, gate_step);
+    default: return launch_dots_tma_inst<DT, 8>(ws, v, ncols, g, smem, grid, hout, nrm2, g_rsq, g_w1sq, gate_step);
+  }
+}
+
+template <class DT, int CPW, bool SPEC>
+static int launch_update_tma_inst(b2a_ws *ws, DT *v, int ncols, const b2a::TmaGeom &g, size_t smem, int grid,
+                                  const DT *h, DT *cout, double *nrm2, const double *g_rsq, const double *g_w1sq,
+                                  int gate_step) {
+  auto kern = b2a::cgs_update_tma_kernel<DT, CPW, SPEC>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    B2A_TRY(set_smem_attr(kern, smem));
+    attr_done = true;
+  }
+  CUtensorMap tm;
+  if (!make_panel_tmap(ws, ncols, g.RT, &tm)) return fail(B2A_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  prof_begin(ws->ctx, B2A_K_UPDATE, (double)(ncols + 2) * ws->n_local * sizeof(DT), gate_step);
+  kern<<<grid, b2a::kTmaThreads, smem, ws->ctx->stream>>>(tm, v, ncols, g, h, reinterpret_cast<DT *>(ws->partials),
+                                                            cout, nrm2, &ws->state->ticket[3], &ws->state->poison,
+                                                            g_rsq, g_w1sq);
+  prof_end(ws->ctx);
+  ws->ctx->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return B2A_OK;
+}
+
+// v -= V h (+ ||v||^2); spec: also cout = V' v_new in the same pass
+template <class DT>
+static int launch_update_tma(b2a_ws *ws, int ncols, DT *v, const DT *h, DT *cout, double *nrm2, bool spec,
+                             const double *g_rsq, const double *g_w1sq, int gate_step, bool reverse) {
+  b2a::TmaGeom g;
+  size_t smem;
+  int grid;
+  if (!tma_geometry(ws, ncols, sizeof(DT), true, reverse, &g, &smem, &grid)) return 1;
+  if (!spec)
+    return launch_update_tma_inst<DT, 1, false>(ws, v, ncols, g, smem, grid, h, cout, nrm2, g_rsq, g_w1sq, gate_step);
+  switch (std::max(1, (ncols + 7) / 8)) {
+    case 1: return launch_update_tma_inst<DT, 1, true>(ws, v, ncols, g, smem, grid, h, cout, nrm2, g_rsq, g_w1sq, gate_step);
+    case 2: return launch_update_tma_inst<DT, 2, true>(ws, v, ncols, g, smem, grid, h, cout, nrm2, g_rsq, g_w1sq, gate_step);
+    case 3: return launch_update_tma_inst<DT, 3, true>(ws, v, ncols, g, smem, grid, h, cout, nrm2, g_rsq, g_w1sq, gate_step);
+    case 4: return launch_update_tma_inst<DT, 4, true>(ws, v, ncols, g, smem, grid, h, cout, nrm2, g_rsq, g_w1sq, gate_step);
+    case 5: return launch_update_tma_inst<DT, 5, true>(ws, v, ncols, g, smem, grid, h, cout, nrm2, g_rsq, g_w1sq, gate_step);
+    case 6: return launch_update_tma_inst<DT, 6, true>(ws, v, ncols, g, smem, grid, h, cout, nrm2, g_rsq, g_w1sq, gate_step);
+    case 7: return launch_update_tma_inst<DT, 7, true>(ws, v, ncols, g, smem, grid, h, cout, nrm2, g_rsq, g_w1sq, gate_step);
+    default: return launch_update_tma_inst<DT, 8, true>(ws, v, ncols, g, smem, grid, h, cout, nrm2, g_rsq, g_w1sq, gate_step);
+  }
+}
+
+static bool tma_path_ok(const b2a_ws *ws, int j, size_t elem) {
+  b2a::TmaGeom g;
+  size_t smem;
+  int grid;
+  return ws->use_tma && get_encode_tiled() != nullptr && j + 1 <= 256 &&
+         tma_geometry(ws, j, elem, false, false, &g, &smem, &grid) &&
+         tma_geometry(ws, j, elem, true, false, &g, &smem, &grid);
+}
+
 // One orthogonalisation of column index j (0-based; panel = columns 0..j-1).
 // mode: 0 Arnoldi step, 1 re-seed, 2 normalise only (j == 0).
 template <class DT> static int enqueue_cgs(b2a_ws *ws, int j, int mode, int step) {
@@ -320,10 +532,24 @@ template <class DT> static int enqueue_cgs(b2a_ws *ws, int j, int mode, int step
   double *w1sq = reinterpret_cast<double *>(h2 + j);
   const size_t hd = (size_t)j * sizeof(DT) / sizeof(double);  // doubles in a j-vector of DT
 
+  const bool tma = tma_path_ok(ws, j, sizeof(DT));
   if (j == 0 || mode == 2) {
-    B2A_TRY(launch_dots<DT>(ws, 0, v, h1, rsq, nullptr, nullptr));
+    if (tma)
+      B2A_TRY(launch_dots_tma<DT>(ws, 0, v, h1, rsq, nullptr, nullptr, 0, false));
+    else
+      B2A_TRY(launch_dots<DT>(ws, 0, v, h1, rsq, nullptr, nullptr));
     B2A_TRY(allreduce_f64(ctx, rsq, 1));
     mode = 2;
+  } else if (tma) {
+    // S1: h = V' v, rnorm^2                                                (expansion.jl:81-84)
+    B2A_TRY(launch_dots_tma<DT>(ws, j, v, h1, rsq, nullptr, nullptr, 0, false));
+    B2A_TRY(allreduce_f64(ctx, h1, hd + 1));
+    // S2: v -= V h, wnorm^2, and speculatively c = V' v_new in the same pass   (expansion.jl:85-88,93)
+    B2A_TRY(launch_update_tma<DT>(ws, j, v, h1, h2, w1sq, true, nullptr, nullptr, 0, true));
+    B2A_TRY(allreduce_f64(ctx, h2, hd + 1));
+    // S3, gated on the device by wnorm < eta * rnorm: v -= V c, wnorm^2       (expansion.jl:91-96)
+    B2A_TRY(launch_update_tma<DT>(ws, j, v, h2, h2, ws->w2sq, false, rsq, w1sq, j, false));
+    B2A_TRY(allreduce_f64(ctx, ws->w2sq, 1));
   } else {
     // pass 1: h = V' v, rnorm^2 ; v -= V h, wnorm^2          (expansion.jl:81-88)
     B2A_TRY(launch_dots<DT>(ws, j, v, h1, rsq, nullptr, nullptr));
@@ -352,13 +578,21 @@ template <class DT> static int enqueue_cgs(b2a_ws *ws, int j, int mode, int step
 // ---- operator -------------------------------------------------------------------
 static double op_bytes(const b2a_op *A);
 
-template <class DT, int LPR>
-static void launch_spmv_vec(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms) {
-  constexpr int U = 4;
+template <class DT, int LPR, int U>
+static void launch_spmv_vec_u(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms) {
   const int64_t threads = cdiv(A->n_local, U) * LPR;
-  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * 8, cdiv(threads, 256)));
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * A->grid_mult, cdiv(threads, 256)));
   b2a::spmv_csr_vector_kernel<DT, LPR, U><<<(unsigned)grid, 256, 0, st>>>(
       A->n_local, A->d_ptr, A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y, poison);
+}
+template <class DT, int LPR>
+static void launch_spmv_vec(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms) {
+  switch (A->rows_in_flight) {
+    case 1: launch_spmv_vec_u<DT, LPR, 1>(A, x, y, poison, st, sms); break;
+    case 2: launch_spmv_vec_u<DT, LPR, 2>(A, x, y, poison, st, sms); break;
+    case 8: launch_spmv_vec_u<DT, LPR, 8>(A, x, y, poison, st, sms); break;
+    default: launch_spmv_vec_u<DT, LPR, 4>(A, x, y, poison, st, sms); break;
+  }
 }
 
 template <class DT, int LPC>
@@ -706,6 +940,12 @@ static int ctx_common(int device, b2a_ctx *c) {
     return fail(B2A_ERR_CUDA, std::string("libb200arnoldi is built for sm_100a only; device is ") + prop.name);
   c->num_sms = prop.multiProcessorCount;
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    cudaMemPool_t pool;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ull;
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   CUDA_TRY(cudaMalloc(&c->d_zero, sizeof(int)));
   CUDA_TRY(cudaMemset(c->d_zero, 0, sizeof(int)));
   return B2A_OK;
@@ -771,6 +1011,7 @@ int b2a_ctx_destroy(b2a_ctx *ctx) {
   for (auto e : ctx->prof_pool) cudaEventDestroy(e);
   if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
   if (ctx->d_zero) cudaFree(ctx->d_zero);
+  for (auto &pc : ctx->pinned_cache) cudaFreeHost(pc.second);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return B2A_OK;
@@ -846,7 +1087,7 @@ static int upload_index(b2a_ctx *ctx, const void *host, int64_t count, int idx_w
   }
   void *tmp = nullptr;
   const size_t bytes = (size_t)count * (idx_width / 8);
-  CUDA_TRY(cudaMalloc(&tmp, bytes));
+  CUDA_TRY(dev_alloc(ctx, &tmp, bytes));
   cudaError_t e = cudaMemcpyAsync(tmp, host, bytes, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) {
     const unsigned grid = (unsigned)std::min<int64_t>(ctx->num_sms * 8, std::max<int64_t>(1, cdiv(count, 256)));
@@ -857,9 +1098,15 @@ static int upload_index(b2a_ctx *ctx, const void *host, int64_t count, int idx_w
     ctx->launches++;
     e = cudaStreamSynchronize(ctx->stream);
   }
-  cudaFree(tmp);
+  dev_free(ctx, tmp);
   CUDA_TRY(e);
   return B2A_OK;
+}
+
+static void op_tuning(b2a_op *op) {
+  if (const char *e = getenv("B2A_SPMV_U")) op->rows_in_flight = atoi(e);
+  if (const char *e = getenv("B2A_SPMV_GRID")) op->grid_mult = std::max(1, atoi(e));
+  if (const char *e = getenv("B2A_SPMV_LPR")) op->lpr = atoi(e);
 }
 
 static int pick_lanes(int64_t nnz, int64_t nrows) {
@@ -874,9 +1121,9 @@ static int pick_lanes(int64_t nnz, int64_t nrows) {
 
 static int op_alloc(b2a_ctx *ctx, b2a_op *op, int64_t nptr) {
   CUDA_TRY(cudaSetDevice(ctx->device));
-  CUDA_TRY(cudaMalloc(&op->d_ptr, (size_t)(nptr + 1) * 8));
-  CUDA_TRY(cudaMalloc(&op->d_idx, (size_t)std::max<int64_t>(op->nnz, 1) * 4));
-  CUDA_TRY(cudaMalloc(&op->d_vals, (size_t)std::max<int64_t>(op->nnz, 1) * dtype_size(op->dtype)));
+  CUDA_TRY(dev_alloc(ctx, reinterpret_cast<void **>(&op->d_ptr), (size_t)(nptr + 1) * 8));
+  CUDA_TRY(dev_alloc(ctx, reinterpret_cast<void **>(&op->d_idx), (size_t)std::max<int64_t>(op->nnz, 1) * 4 + 64));
+  CUDA_TRY(dev_alloc(ctx, &op->d_vals, (size_t)std::max<int64_t>(op->nnz, 1) * dtype_size(op->dtype) + 64));
   return B2A_OK;
 }
 
@@ -884,9 +1131,9 @@ int b2a_op_destroy(b2a_op *op) {
   if (!op) return B2A_OK;
   if (op->owns) {
     cudaSetDevice(op->ctx->device);
-    if (op->d_ptr) cudaFree(op->d_ptr);
-    if (op->d_idx) cudaFree(op->d_idx);
-    if (op->d_vals) cudaFree(op->d_vals);
+    dev_free(op->ctx, op->d_ptr);
+    dev_free(op->ctx, op->d_idx);
+    dev_free(op->ctx, op->d_vals);
   }
   delete op;
   return B2A_OK;
@@ -919,6 +1166,7 @@ int b2a_csr_create(b2a_ctx *ctx, int dtype, int64_t n_rows_local, int64_t n_glob
   op->row_offset = row_offset;
   op->nnz = nnz;
   op->lpr = pick_lanes(nnz, n_rows_local);
+  op_tuning(op);
   int s = op_alloc(ctx, op, n_rows_local);
   if (s == B2A_OK) s = upload_index(ctx, rowptr, n_rows_local + 1, idx_width, idx_base, op->d_ptr, nullptr);
   if (s == B2A_OK) s = upload_index(ctx, colind, nnz, idx_width, idx_base, nullptr, op->d_idx);
@@ -1049,10 +1297,10 @@ int b2a_op_bytes(b2a_op *op, double *bytes) {
 int b2a_ws_destroy(b2a_ws *ws) {
   if (!ws) return B2A_OK;
   cudaSetDevice(ws->ctx->device);
-  void *ptrs[] = {ws->dV, ws->dH, ws->dinfo, ws->hb1, ws->hb2, ws->w2sq, ws->partials, ws->partials2, ws->state, ws->dQ, ws->xfull};
-  for (void *p : ptrs)
-    if (p) cudaFree(p);
-  if (ws->pinned) cudaFreeHost(ws->pinned);
+  dev_free(ws->ctx, ws->dV);
+  dev_free(ws->ctx, ws->arena);
+  dev_free(ws->ctx, ws->xfull);
+  pinned_put(ws->ctx, ws->pinned, ws->pinned_bytes);
   delete ws;
   return B2A_OK;
 }
@@ -1075,14 +1323,14 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
   if (ctx->world > 1) {
     // share the row partition; uniform blocks (all but the last rank equal) use all-gather
     int64_t *d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, sizeof(int64_t) * 2 * (ctx->world + 1)));
+    CUDA_TRY(dev_alloc(ctx, reinterpret_cast<void **>(&d), sizeof(int64_t) * 2 * (ctx->world + 1)));
     int64_t mine[2] = {row_offset, n_local};
     CUDA_TRY(cudaMemcpyAsync(d, mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
     NCCL_TRY(g_nccl.AllGather(d, d + 2, 2, ncclInt64, ctx->comm, ctx->stream));
     std::vector<int64_t> all(2 * ctx->world);
     CUDA_TRY(cudaMemcpyAsync(all.data(), d + 2, sizeof(int64_t) * 2 * ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d);
+    dev_free(ctx, d);
     int64_t expect = 0;
     const int64_t blk = all[1];
     ws->uniform_partition = true;
@@ -1097,34 +1345,52 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
     if (expect != n_global) return fail(B2A_ERR_DIMENSION, "row blocks do not add up to n_global");
     if (ws->uniform_partition) ld_rows = std::max(ld_rows, blk);  // all-gather reads blk rows from every rank
   }
-  ws->ld = round_up(std::max<int64_t>(ld_rows, 1), 16);
-  CUDA_TRY(cudaMalloc(&ws->dV, (size_t)ws->ld * m1 * es));
+  // multiple of 1024 rows: every TMA tile (RT | 1024) can be loaded full-size; padding rows stay zero
+  ws->ld = round_up(std::max<int64_t>(ld_rows, 1), 1024);
+  ws->use_tma = !(getenv("B2A_NO_TMA") && getenv("B2A_NO_TMA")[0] == '1');
+  if (const char *e = getenv("B2A_TMA_RT_DOTS")) ws->tune_rt_dots = atoi(e);
+  if (const char *e = getenv("B2A_TMA_RT_UPD")) ws->tune_rt_upd = atoi(e);
+  if (const char *e = getenv("B2A_TMA_STAGES")) ws->tune_stages = atoi(e);
+  CUDA_TRY(dev_alloc(ctx, &ws->dV, (size_t)ws->ld * m1 * es));
   CUDA_TRY(cudaMemsetAsync(ws->dV, 0, (size_t)ws->ld * m1 * es, ctx->stream));  // padding rows stay zero forever
   ws->H.assign((size_t)m1 * maxdim * es, 0);
   ws->Q.assign((size_t)maxdim * maxdim * es, 0);
   ws->dots_grid_max = 2 * ctx->num_sms;
   ws->upd_grid_max = 8 * ctx->num_sms;
-  CUDA_TRY(cudaMalloc(&ws->dH, (size_t)m1 * maxdim * es));
-  CUDA_TRY(cudaMemsetAsync(ws->dH, 0, (size_t)m1 * maxdim * es, ctx->stream));
-  CUDA_TRY(cudaMalloc(&ws->dinfo, sizeof(int) * (m1 + 1)));
-  CUDA_TRY(cudaMemsetAsync(ws->dinfo, 0, sizeof(int) * (m1 + 1), ctx->stream));
-  CUDA_TRY(cudaMalloc(&ws->hb1, (size_t)(m1 + 1) * es + 16));
-  CUDA_TRY(cudaMalloc(&ws->hb2, (size_t)(m1 + 1) * es + 16));
-  CUDA_TRY(cudaMemsetAsync(ws->hb1, 0, (size_t)(m1 + 1) * es + 16, ctx->stream));
-  CUDA_TRY(cudaMemsetAsync(ws->hb2, 0, (size_t)(m1 + 1) * es + 16, ctx->stream));
-  CUDA_TRY(cudaMalloc(&ws->w2sq, 16));
-  CUDA_TRY(cudaMemsetAsync(ws->w2sq, 0, 16, ctx->stream));
-  CUDA_TRY(cudaMalloc(&ws->partials, (size_t)(66) * ws->dots_grid_max * es));
-  CUDA_TRY(cudaMalloc(&ws->partials2, sizeof(double) * ws->upd_grid_max));
-  CUDA_TRY(cudaMalloc(&ws->state, sizeof(b2a::SweepState)));
-  CUDA_TRY(cudaMemsetAsync(ws->state, 0, sizeof(b2a::SweepState), ctx->stream));
-  CUDA_TRY(cudaMalloc(&ws->dQ, (size_t)std::max(maxdim * maxdim, 1) * es));
+  // all small scratch arrays live in one zero-initialised arena (256-byte aligned slices)
+  size_t off = 0;
+  auto carve = [&](size_t bytes) {
+    const size_t at = off;
+    off += (bytes + 255) / 256 * 256;
+    return at;
+  };
+  const size_t o_dH = carve((size_t)m1 * maxdim * es);
+  const size_t o_info = carve(sizeof(int) * (m1 + 1));
+  const size_t o_hb1 = carve((size_t)(m1 + 1) * es + 16);
+  const size_t o_hb2 = carve((size_t)(m1 + 1) * es + 16);
+  const size_t o_w2 = carve(16);
+  const size_t o_part = carve((size_t)66 * ws->dots_grid_max * es);
+  const size_t o_part2 = carve(sizeof(double) * ws->upd_grid_max);
+  const size_t o_state = carve(sizeof(b2a::SweepState));
+  const size_t o_dQ = carve((size_t)std::max(maxdim * maxdim, 1) * es);
+  CUDA_TRY(dev_alloc(ctx, &ws->arena, off));
+  CUDA_TRY(cudaMemsetAsync(ws->arena, 0, off, ctx->stream));
+  char *base = reinterpret_cast<char *>(ws->arena);
+  ws->dH = base + o_dH;
+  ws->dinfo = reinterpret_cast<int *>(base + o_info);
+  ws->hb1 = base + o_hb1;
+  ws->hb2 = base + o_hb2;
+  ws->w2sq = reinterpret_cast<double *>(base + o_w2);
+  ws->partials = base + o_part;
+  ws->partials2 = reinterpret_cast<double *>(base + o_part2);
+  ws->state = reinterpret_cast<b2a::SweepState *>(base + o_state);
+  ws->dQ = base + o_dQ;
   if (ctx->world > 1) {
     const int64_t nx = ws->uniform_partition ? ws->all_counts[0] * ctx->world : n_global;
-    CUDA_TRY(cudaMalloc(&ws->xfull, (size_t)nx * es));
+    CUDA_TRY(dev_alloc(ctx, &ws->xfull, (size_t)nx * es));
   }
-  ws->pinned_bytes = (size_t)m1 * maxdim * es + sizeof(int) * (m1 + 1) + sizeof(b2a::SweepState) + 64;
-  CUDA_TRY(cudaMallocHost(&ws->pinned, ws->pinned_bytes));
+  const size_t want = (size_t)m1 * maxdim * es + sizeof(int) * (m1 + 1) + sizeof(b2a::SweepState) + 64;
+  CUDA_TRY(pinned_get(ctx, want, &ws->pinned, &ws->pinned_bytes));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return B2A_OK;
 }
@@ -1310,10 +1576,10 @@ int b2a_basis_times(b2a_ws *ws, int nconv, const double *Y, int ldy, double *X, 
     for (int c = 0; c < nconv; ++c) Yp[(size_t)o * nconv + c] = cplx(Y[2 * ((size_t)o * ldy + c)], Y[2 * ((size_t)o * ldy + c) + 1]);
   cdouble *dY = nullptr, *dX = nullptr;
   const int64_t n = ws->n_local;
-  CUDA_TRY(cudaMalloc(&dY, sizeof(cdouble) * nconv * nconv));
-  cudaError_t e = cudaMalloc(&dX, sizeof(cdouble) * (size_t)std::max<int64_t>(n, 1) * nconv);
+  CUDA_TRY(dev_alloc(ctx, reinterpret_cast<void **>(&dY), sizeof(cdouble) * nconv * nconv));
+  cudaError_t e = dev_alloc(ctx, reinterpret_cast<void **>(&dX), sizeof(cdouble) * (size_t)std::max<int64_t>(n, 1) * nconv);
   if (e != cudaSuccess) {
-    cudaFree(dY);
+    dev_free(ctx, dY);
     CUDA_TRY(e);
   }
   e = cudaMemcpyAsync(dY, Yp.data(), sizeof(cdouble) * nconv * nconv, cudaMemcpyHostToDevice, ctx->stream);
@@ -1329,8 +1595,8 @@ int b2a_basis_times(b2a_ws *ws, int nconv, const double *Y, int ldy, double *X, 
   if (e == cudaSuccess)
     e = cudaMemcpy2DAsync(X, (size_t)ldx * 16, dX, (size_t)n * 16, (size_t)n * 16, nconv, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(dY);
-  cudaFree(dX);
+  dev_free(ctx, dY);
+  dev_free(ctx, dX);
   CUDA_TRY(e);
   return B2A_OK;
 }
