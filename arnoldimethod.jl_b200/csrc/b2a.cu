@@ -33,6 +33,7 @@
 #include "kernels_cgs_tma.cuh"
 #include "kernels_rotate.cuh"
 #include "kernels_spmv.cuh"
+#include "kernels_spmv_tma.cuh"
 
 using b2a::cdouble;
 using b2a::host::cplx;
@@ -222,7 +223,11 @@ struct b2a_op {
   void *d_vals = nullptr;
   bool owns = true;
   int lpr = 8;  // lanes per row (column)
-  int rows_in_flight = 4, grid_mult = 8;  // SpMV tuning (env B2A_SPMV_U / B2A_SPMV_GRID)
+  int rows_in_flight = 2, grid_mult = 16;  // SpMV tuning (env B2A_SPMV_U / B2A_SPMV_GRID)
+  // TMA-stream kernel: row tiles built at upload (kernels_spmv_tma.cuh)
+  int32_t *d_tile_row = nullptr;
+  int ntiles = 0, tma_stages = 0;
+  bool use_tma = false;
   b2a_matvec_fn fn = nullptr;
   void *user = nullptr;
 };
@@ -603,6 +608,39 @@ static void launch_spmv_csc(b2a_op *A, const DT *x, DT *y, const int *poison, cu
       A->n_global, A->d_ptr, A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y, poison);
 }
 
+template <class DT, int LPR>
+static int launch_spmv_tma_inst(b2a_op *A, const DT *x, DT *y, const int *poison, b2a_ctx *ctx) {
+  auto kern = b2a::spmv_csr_tma_kernel<DT, LPR>;
+  const size_t stage = b2a::SpmvStage<DT>::bytes;
+  // two CTAs per SM (two-stage rings): while one CTA reduces rows the other has its gathers in flight
+  const int grid = std::min(2 * ctx->num_sms, A->ntiles);
+  const int tpc = (int)cdiv(A->ntiles, grid);
+  const int g2 = (int)cdiv(A->ntiles, tpc);
+  int stages = (int)std::min<size_t>(b2a::kSpmvMaxStages, (kTmaSmemBudget / 2 - 128) / stage);
+  if (A->tma_stages >= 2) stages = A->tma_stages;
+  stages = std::max(2, std::min(stages, std::max(2, tpc)));
+  const size_t smem = 128 + (size_t)stages * stage;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBudget));
+    attr_done = true;
+  }
+  kern<<<g2, b2a::kTmaThreads, smem, ctx->stream>>>(A->n_local, A->d_ptr, A->d_idx,
+                                                      reinterpret_cast<const DT *>(A->d_vals), A->d_tile_row, A->ntiles,
+                                                      tpc, stages, x, y, poison);
+  return B2A_OK;
+}
+template <class DT> static int launch_spmv_tma(b2a_op *A, const DT *x, DT *y, const int *poison, b2a_ctx *ctx) {
+  switch (A->lpr) {
+    case 1:
+    case 2: return launch_spmv_tma_inst<DT, 2>(A, x, y, poison, ctx);
+    case 4: return launch_spmv_tma_inst<DT, 4>(A, x, y, poison, ctx);
+    case 8: return launch_spmv_tma_inst<DT, 8>(A, x, y, poison, ctx);
+    case 16: return launch_spmv_tma_inst<DT, 16>(A, x, y, poison, ctx);
+    default: return launch_spmv_tma_inst<DT, 32>(A, x, y, poison, ctx);
+  }
+}
+
 // y = A x for the local rows; x_local / y are workspace columns.
 template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, int jdst0) {
   b2a_ctx *ctx = ws->ctx;
@@ -643,6 +681,8 @@ template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, 
       case 16: launch_spmv_csc<DT, 16>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
       default: launch_spmv_csc<DT, 32>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
     }
+  } else if (A->use_tma) {
+    B2A_TRY(launch_spmv_tma<DT>(A, x, y, poison, ctx));
   } else {
     switch (A->lpr) {
       case 1: {
@@ -1107,21 +1147,59 @@ static void op_tuning(b2a_op *op) {
   if (const char *e = getenv("B2A_SPMV_U")) op->rows_in_flight = atoi(e);
   if (const char *e = getenv("B2A_SPMV_GRID")) op->grid_mult = std::max(1, atoi(e));
   if (const char *e = getenv("B2A_SPMV_LPR")) op->lpr = atoi(e);
+  if (const char *e = getenv("B2A_SPMV_STAGES")) op->tma_stages = atoi(e);
 }
 
+extern "C++" {
+// Cut the rows into tiles for the TMA-stream kernel: even row boundaries, at most kSpmvMaxRows rows
+// and kSpmvMaxNnz non-zeros (plus alignment slack) per tile.  Returns false if some row is too long.
+template <class RP> static bool build_row_tiles(RP rp, int64_t n_rows, int max_nnz, std::vector<int32_t> &tiles) {
+  tiles.clear();
+  if (n_rows >= 2147483000LL) return false;
+  int64_t r = 0;
+  while (r < n_rows) {
+    tiles.push_back((int32_t)r);
+    const int64_t nz0 = rp(r);
+    int64_t r1 = r;
+    while (r1 < n_rows && r1 - r < b2a::kSpmvMaxRows) {
+      const int64_t nxt = std::min<int64_t>(r1 + 2, n_rows);
+      if (rp(nxt) - nz0 > max_nnz) break;
+      r1 = nxt;
+    }
+    if (r1 == r) return false;  // a row pair with more than kSpmvMaxNnz entries
+    r = r1;
+  }
+  tiles.push_back((int32_t)n_rows);
+  return true;
+}
+
+}  // extern "C++"
+
+static int upload_tiles(b2a_ctx *ctx, b2a_op *op, const std::vector<int32_t> &tiles) {
+  op->ntiles = (int)tiles.size() - 1;
+  CUDA_TRY(dev_alloc(ctx, reinterpret_cast<void **>(&op->d_tile_row), tiles.size() * sizeof(int32_t)));
+  CUDA_TRY(cudaMemcpyAsync(op->d_tile_row, tiles.data(), tiles.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  // opt-in (B2A_SPMV_TMA=1): measured on B200 the staged stream is gather-latency bound and loses to
+  // the occupancy-driven LDG kernel (191 vs 98 us at cfg 2, 220 vs 146 us on a 160^3 Laplacian)
+  op->use_tma = op->ntiles > 0 && getenv("B2A_SPMV_TMA") && getenv("B2A_SPMV_TMA")[0] == '1';
+  return B2A_OK;
+}
+
+// Lanes per row of the CSR vector kernel.  Measured on B200 (tools/spmvbench.py sweeps): about four
+// entries per lane is best - 7-point Laplacian: LPR 2 = 94 us vs LPR 8 = 146 us (n = 4.1e6);
+// 16 nnz/row random: LPR 4 = 91 us vs LPR 16 = 106 us; ComplexF64 20 nnz/row: LPR 4 = 120 us vs 193 us.
 static int pick_lanes(int64_t nnz, int64_t nrows) {
   const double avg = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
   if (avg <= 1.5) return 1;
-  if (avg <= 3.0) return 2;
-  if (avg <= 6.0) return 4;
-  if (avg <= 12.0) return 8;
-  if (avg <= 24.0) return 16;
-  return 32;
+  int lpr = 2;
+  while (lpr < 32 && lpr * 2 <= avg / 4.0) lpr *= 2;
+  return lpr;
 }
 
 static int op_alloc(b2a_ctx *ctx, b2a_op *op, int64_t nptr) {
   CUDA_TRY(cudaSetDevice(ctx->device));
-  CUDA_TRY(dev_alloc(ctx, reinterpret_cast<void **>(&op->d_ptr), (size_t)(nptr + 1) * 8));
+  CUDA_TRY(dev_alloc(ctx, reinterpret_cast<void **>(&op->d_ptr), (size_t)(nptr + 1) * 8 + 64));
   CUDA_TRY(dev_alloc(ctx, reinterpret_cast<void **>(&op->d_idx), (size_t)std::max<int64_t>(op->nnz, 1) * 4 + 64));
   CUDA_TRY(dev_alloc(ctx, &op->d_vals, (size_t)std::max<int64_t>(op->nnz, 1) * dtype_size(op->dtype) + 64));
   return B2A_OK;
@@ -1134,6 +1212,10 @@ int b2a_op_destroy(b2a_op *op) {
     dev_free(op->ctx, op->d_ptr);
     dev_free(op->ctx, op->d_idx);
     dev_free(op->ctx, op->d_vals);
+  }
+  if (op->d_tile_row) {
+    cudaSetDevice(op->ctx->device);
+    dev_free(op->ctx, op->d_tile_row);
   }
   delete op;
   return B2A_OK;
@@ -1175,6 +1257,16 @@ int b2a_csr_create(b2a_ctx *ctx, int dtype, int64_t n_rows_local, int64_t n_glob
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) s = fail(B2A_ERR_CUDA, cudaGetErrorString(e));
   }
+  if (s == B2A_OK && n_rows_local > 0) {
+    std::vector<int32_t> tiles;
+    bool ok;
+    const int max_nnz = dtype == B2A_C64 ? b2a::SpmvTile<cdouble>::max_nnz : b2a::SpmvTile<double>::max_nnz;
+    if (idx_width == 32)
+      ok = build_row_tiles([&](int64_t r) { return (int64_t) reinterpret_cast<const int32_t *>(rowptr)[r] - idx_base; }, n_rows_local, max_nnz, tiles);
+    else
+      ok = build_row_tiles([&](int64_t r) { return reinterpret_cast<const int64_t *>(rowptr)[r] - idx_base; }, n_rows_local, max_nnz, tiles);
+    if (ok) s = upload_tiles(ctx, op, tiles);
+  }
   if (s != B2A_OK) {
     b2a_op_destroy(op);
     return s;
@@ -1201,6 +1293,27 @@ int b2a_csr_create_device(b2a_ctx *ctx, int dtype, int64_t n_rows_local, int64_t
   op->d_idx = const_cast<int32_t *>(d_colind);
   op->d_vals = const_cast<void *>(d_vals);
   op->owns = false;
+  op_tuning(op);
+  if (n_rows_local > 0) {
+    // NOTE: the TMA-stream kernel reads 16-byte aligned supersets of the colind / vals slices, i.e. up
+    // to 3 entries past nnz: borrowed arrays must be padded accordingly, else set B2A_SPMV_TMA=0.
+    std::vector<int64_t> rp((size_t)n_rows_local + 1);
+    cudaError_t e = cudaMemcpyAsync(rp.data(), d_rowptr, rp.size() * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      delete op;
+      CUDA_TRY(e);
+    }
+    std::vector<int32_t> tiles;
+    const int max_nnz = dtype == B2A_C64 ? b2a::SpmvTile<cdouble>::max_nnz : b2a::SpmvTile<double>::max_nnz;
+    if (getenv("B2A_SPMV_TMA_BORROWED") && build_row_tiles([&](int64_t r) { return rp[(size_t)r]; }, n_rows_local, max_nnz, tiles)) {
+      int s2 = upload_tiles(ctx, op, tiles);
+      if (s2 != B2A_OK) {
+        delete op;
+        return s2;
+      }
+    }
+  }
   *out = op;
   return B2A_OK;
 }

@@ -22,7 +22,6 @@ template <class T> __device__ __forceinline__ T ld_ro(const T *p);
 template <> __device__ __forceinline__ double ld_ro<double>(const double *p) { return __ldg(p); }
 template <> __device__ __forceinline__ cdouble ld_ro<cdouble>(const cdouble *p) { return __ldg(p); }
 
-template <class T, int LPR> __device__ __forceinline__ T group_sum(T v);
 template <int LPR> __device__ __forceinline__ double group_sum_d(double v) {
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -39,7 +38,10 @@ __global__ void __launch_bounds__(256)
   const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / LPR;
 
-  for (int64_t rbase = group; rbase < n_rows; rbase += ngroups * U) {
+  // loop bound uniform over the grid (rbase0 is the same for every thread) so that all lanes of a
+  // warp reach the full-mask shuffles; rows past the end are predicated off
+  for (int64_t rbase0 = 0; rbase0 < n_rows; rbase0 += ngroups * U) {
+    const int64_t rbase = rbase0 + group;
     int64_t rs[U], re[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {

@@ -332,3 +332,19 @@ def test_callback_operator(ctx):
     V, H = ws.V, np.array(ws.H)
     Ad = sp.diags(d) + 0.1 * sp.csr_matrix((np.ones(n), (np.arange(n), (np.arange(n) - 1) % n)), shape=(n, n))
     assert np.linalg.norm(Ad @ V[:, :12] - V @ H) < 1e-12
+
+
+def test_spmv_tma_stream_kernel_opt_in(ctx, monkeypatch):
+    """The TMA-staged CSR-stream kernel (opt-in, B2A_SPMV_TMA=1) gives the same result as SciPy."""
+    monkeypatch.setenv("B2A_SPMV_TMA", "1")
+    rng = np.random.default_rng(77)
+    for T, k, ragged in [(np.float64, 16, False), (np.float64, 7, True), (np.complex128, 20, True), (np.float64, 3, True)]:
+        n = 30011
+        A = random_csr(rng, T, n, k, ragged)
+        op = b2a.Operator.from_matrix(ctx, A)
+        ws = b2a.ArnoldiWorkspace(n, 2, dtype=T, ctx=ctx)
+        x = randn(rng, T, n)
+        ws.set_col(1, x)
+        ws.matvec(op, 1, 2)
+        y = ws.get_cols(2, 1)[:, 0]
+        assert np.abs(y - A @ x).max() <= 64 * EPS * (abs(A) @ abs(x)).max()

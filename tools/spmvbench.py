@@ -36,10 +36,11 @@ def main():
     ctx = b2a.default_context()
     configs = [dict()]
     if "--sweep" in sys.argv:
+        lprs = [int(v) for v in os.environ.get("SWEEP_LPR", "8,16").split(",")]
         configs = [dict(B2A_SPMV_U=str(u), B2A_SPMV_GRID=str(g), B2A_SPMV_LPR=str(l))
-                   for l in (8, 16) for u in (2, 4, 8) for g in (8, 16)]
+                   for l in lprs for u in (2, 4, 8) for g in (8, 16)]
     for cfg in configs:
-        for k_ in ("B2A_SPMV_U", "B2A_SPMV_GRID", "B2A_SPMV_LPR", "B2A_SPMV_TMA"):
+        for k_ in ("B2A_SPMV_U", "B2A_SPMV_GRID", "B2A_SPMV_LPR"):
             os.environ.pop(k_, None)
         os.environ.update(cfg)
         op = b2a.Operator.from_matrix(ctx, A)
