@@ -146,9 +146,14 @@ class Operator:
         data = np.ascontiguousarray(data, dtype=dt)
         indptr = np.ascontiguousarray(indptr)
         indices = np.ascontiguousarray(indices)
-        if indptr.dtype != indices.dtype or indptr.dtype not in (np.int32, np.int64):
-            wide = np.int64 if (indptr.dtype.itemsize > 4 or indices.dtype.itemsize > 4) else np.int32
-            indptr, indices = indptr.astype(wide), indices.astype(wide)
+        if indices.dtype not in (np.int32, np.int64):
+            indices = indices.astype(np.int64 if indices.dtype.itemsize > 4 else np.int32)
+        if indptr.dtype != indices.dtype:
+            # one index width crosses the ABI: convert the SMALL array (rowptr, n+1 entries), never the
+            # nnz-sized one - unless the row pointers do not fit 32 bits
+            if indices.dtype == np.int32 and int(indptr[-1]) + int(idx_base) >= 2**31 - 1:
+                indices = indices.astype(np.int64)
+            indptr = indptr.astype(indices.dtype)
         n_local = indptr.shape[0] - 1
         h = C.c_void_p()
         L.check(

@@ -34,6 +34,7 @@
 #include "kernels_rotate.cuh"
 #include "kernels_spmv.cuh"
 #include "kernels_spmv_tma.cuh"
+#include "peer_comm.cuh"
 
 using b2a::cdouble;
 using b2a::host::cplx;
@@ -135,6 +136,14 @@ struct b2a_ctx {
   double prof_ms[B2A_K_COUNT] = {0}, prof_bytes[B2A_K_COUNT] = {0};
   // pinned host staging buffers are expensive to create: recycled across workspaces
   std::vector<std::pair<size_t, char *>> pinned_cache;
+  // NVLink peer communication block (cudaMalloc + CUDA IPC): created once, re-used by every workspace
+  // whose needs fit (creating it is a collective with ~ms cost); see peer_setup()
+  char *peer_local = nullptr;
+  std::vector<void *> peer_opened;
+  b2a::PeerView peer_view;   // P == 1: not available
+  int peer_slot = 0;
+  size_t peer_x_bytes = 0;
+  bool peer_busy = false;    // handed to a live workspace
 };
 
 // Device memory comes from the device's stream-ordered pool (cudaMallocAsync) with an unlimited
@@ -259,6 +268,11 @@ struct b2a_ws {
   std::vector<int64_t> all_offsets, all_counts;  // row partition over ranks
   bool uniform_partition = true;
   bool use_tma = true;  // TMA-pipelined Gram-Schmidt sweeps (B2A_NO_TMA=1 selects the LDG kernels)
+  // in-kernel collectives over NVLink peer memory (peer_comm.cuh); B2A_NO_PEER=1 falls back to NCCL
+  b2a::PeerView peer;            // P == 1 when disabled; the block itself is owned by the context
+  bool peer_borrowed = false;
+  int finish_grid_mult = 4;
+  int x_pushed_col = -1;  // 0-based column whose normalised content currently sits in every rank's x buffer
   int tune_rt_dots = 0, tune_rt_upd = 0, tune_stages = 0, tune_grid_mult = 1;  // experiment overrides (env)
 };
 
@@ -447,7 +461,7 @@ static int launch_dots_tma_inst(b2a_ws *ws, const DT *v, int ncols, const b2a::T
   prof_begin(ws->ctx, B2A_K_DOTS, (double)(ncols + 1) * ws->n_local * sizeof(DT), gate_step);
   kern<<<grid, b2a::kTmaThreads, smem, ws->ctx->stream>>>(tm, ncols, g, reinterpret_cast<DT *>(ws->partials), hout,
                                                             nrm2, &ws->state->ticket[2], &ws->state->poison, g_rsq,
-                                                            g_w1sq);
+                                                            g_w1sq, ws->peer);
   prof_end(ws->ctx);
   ws->ctx->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -488,7 +502,7 @@ static int launch_update_tma_inst(b2a_ws *ws, DT *v, int ncols, const b2a::TmaGe
   prof_begin(ws->ctx, B2A_K_UPDATE, (double)(ncols + 2) * ws->n_local * sizeof(DT), gate_step);
   kern<<<grid, b2a::kTmaThreads, smem, ws->ctx->stream>>>(tm, v, ncols, g, h, reinterpret_cast<DT *>(ws->partials),
                                                             cout, nrm2, &ws->state->ticket[3], &ws->state->poison,
-                                                            g_rsq, g_w1sq);
+                                                            g_rsq, g_w1sq, ws->peer);
   prof_end(ws->ctx);
   ws->ctx->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -538,23 +552,26 @@ template <class DT> static int enqueue_cgs(b2a_ws *ws, int j, int mode, int step
   const size_t hd = (size_t)j * sizeof(DT) / sizeof(double);  // doubles in a j-vector of DT
 
   const bool tma = tma_path_ok(ws, j, sizeof(DT));
+  // multi-GPU: the TMA kernels finish their own all-reduce over NVLink peer memory (peer_comm.cuh);
+  // otherwise a host-launched NCCL all-reduce follows each reduction kernel
+  const bool fused = tma && ws->peer.P > 1;
   if (j == 0 || mode == 2) {
     if (tma)
       B2A_TRY(launch_dots_tma<DT>(ws, 0, v, h1, rsq, nullptr, nullptr, 0, false));
     else
       B2A_TRY(launch_dots<DT>(ws, 0, v, h1, rsq, nullptr, nullptr));
-    B2A_TRY(allreduce_f64(ctx, rsq, 1));
+    if (!fused) B2A_TRY(allreduce_f64(ctx, rsq, 1));
     mode = 2;
   } else if (tma) {
     // S1: h = V' v, rnorm^2                                                (expansion.jl:81-84)
     B2A_TRY(launch_dots_tma<DT>(ws, j, v, h1, rsq, nullptr, nullptr, 0, false));
-    B2A_TRY(allreduce_f64(ctx, h1, hd + 1));
+    if (!fused) B2A_TRY(allreduce_f64(ctx, h1, hd + 1));
     // S2: v -= V h, wnorm^2, and speculatively c = V' v_new in the same pass   (expansion.jl:85-88,93)
     B2A_TRY(launch_update_tma<DT>(ws, j, v, h1, h2, w1sq, true, nullptr, nullptr, 0, true));
-    B2A_TRY(allreduce_f64(ctx, h2, hd + 1));
+    if (!fused) B2A_TRY(allreduce_f64(ctx, h2, hd + 1));
     // S3, gated on the device by wnorm < eta * rnorm: v -= V c, wnorm^2       (expansion.jl:91-96)
     B2A_TRY(launch_update_tma<DT>(ws, j, v, h2, h2, ws->w2sq, false, rsq, w1sq, j, false));
-    B2A_TRY(allreduce_f64(ctx, ws->w2sq, 1));
+    if (!fused) B2A_TRY(allreduce_f64(ctx, ws->w2sq, 1));
   } else {
     // pass 1: h = V' v, rnorm^2 ; v -= V h, wnorm^2          (expansion.jl:81-88)
     B2A_TRY(launch_dots<DT>(ws, j, v, h1, rsq, nullptr, nullptr));
@@ -569,13 +586,17 @@ template <class DT> static int enqueue_cgs(b2a_ws *ws, int j, int mode, int step
   }
   constexpr int PV = b2a::Scalar<DT>::per_vec;
   const int64_t nvec = cdiv(ws->n_local, PV);
-  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(ws->upd_grid_max, cdiv(nvec, 256)));
+  // 4 vectors per thread and pass; at most 4 CTAs per SM (one system-scope fence per CTA when pushing)
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * ws->finish_grid_mult, cdiv(nvec, 256 * 4)));
   DT *Hcol = reinterpret_cast<DT *>(ws->dH) + (int64_t)(std::max(j, 1) - 1) * (ws->maxdim + 1);
   prof_begin(ctx, B2A_K_FINISH, 2.0 * ws->n_local * sizeof(DT));
+  const int push = (mode == 0 && ws->peer.P > 1) ? 1 : 0;  // Arnoldi step: the new column is the next mat-vec input
   b2a::cgs_finish_kernel<DT><<<(unsigned)grid, 256, 0, ctx->stream>>>(
-      v, ws->n_local, j, h1, h2, rsq, w1sq, ws->w2sq, Hcol, ws->dinfo + j, ws->state, step, mode);
+      v, ws->n_local, j, h1, h2, rsq, w1sq, ws->w2sq, Hcol, ws->dinfo + j, ws->state, step, mode, ws->peer,
+      ws->row_offset, push);
   prof_end(ctx);
   ctx->launches++;
+  ws->x_pushed_col = push ? j : -1;
   CUDA_TRY(cudaGetLastError());
   return B2A_OK;
 }
@@ -583,20 +604,26 @@ template <class DT> static int enqueue_cgs(b2a_ws *ws, int j, int mode, int step
 // ---- operator -------------------------------------------------------------------
 static double op_bytes(const b2a_op *A);
 
+struct XWait {
+  b2a::PeerView pv;
+  int wait = 0;
+};
 template <class DT, int LPR, int U>
-static void launch_spmv_vec_u(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms) {
+static void launch_spmv_vec_u(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms,
+                              const XWait &xw) {
   const int64_t threads = cdiv(A->n_local, U) * LPR;
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * A->grid_mult, cdiv(threads, 256)));
   b2a::spmv_csr_vector_kernel<DT, LPR, U><<<(unsigned)grid, 256, 0, st>>>(
-      A->n_local, A->d_ptr, A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y, poison);
+      A->n_local, A->d_ptr, A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y, poison, xw.pv, xw.wait);
 }
 template <class DT, int LPR>
-static void launch_spmv_vec(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms) {
+static void launch_spmv_vec(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms,
+                            const XWait &xw) {
   switch (A->rows_in_flight) {
-    case 1: launch_spmv_vec_u<DT, LPR, 1>(A, x, y, poison, st, sms); break;
-    case 2: launch_spmv_vec_u<DT, LPR, 2>(A, x, y, poison, st, sms); break;
-    case 8: launch_spmv_vec_u<DT, LPR, 8>(A, x, y, poison, st, sms); break;
-    default: launch_spmv_vec_u<DT, LPR, 4>(A, x, y, poison, st, sms); break;
+    case 1: launch_spmv_vec_u<DT, LPR, 1>(A, x, y, poison, st, sms, xw); break;
+    case 4: launch_spmv_vec_u<DT, LPR, 4>(A, x, y, poison, st, sms, xw); break;
+    case 8: launch_spmv_vec_u<DT, LPR, 8>(A, x, y, poison, st, sms, xw); break;
+    default: launch_spmv_vec_u<DT, LPR, 2>(A, x, y, poison, st, sms, xw); break;
   }
 }
 
@@ -653,7 +680,21 @@ template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, 
     return B2A_OK;
   }
   const DT *x = xl;
-  if (ctx->world > 1) {
+  XWait xw;
+  if (ctx->world > 1 && ws->peer.P > 1) {
+    // push model over NVLink peer memory: normally the normalising cgs_finish kernel of the previous step
+    // has already pushed this column into every rank's x buffer; otherwise push it explicitly
+    if (ws->x_pushed_col != jsrc0) {
+      const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 4, cdiv(ws->n_local, 256)));
+      b2a::xpush_kernel<DT><<<(unsigned)grid, 256, 0, ctx->stream>>>(xl, ws->n_local, ws->state, ws->peer, ws->row_offset);
+      ctx->launches++;
+      CUDA_TRY(cudaGetLastError());
+      ws->x_pushed_col = jsrc0;
+    }
+    xw.pv = ws->peer;
+    xw.wait = 1;
+    x = reinterpret_cast<const DT *>(ws->peer.peer[ws->peer.rank] + ws->peer.off_x);
+  } else if (ctx->world > 1) {
     // x-exchange: every shard needs (in general) all of x.  Uniform partitions use one
     // all-gather; ragged ones a group of broadcasts.
     DT *xf = reinterpret_cast<DT *>(ws->xfull);
@@ -681,21 +722,21 @@ template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, 
       case 16: launch_spmv_csc<DT, 16>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
       default: launch_spmv_csc<DT, 32>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
     }
-  } else if (A->use_tma) {
+  } else if (A->use_tma && ctx->world == 1) {
     B2A_TRY(launch_spmv_tma<DT>(A, x, y, poison, ctx));
   } else {
     switch (A->lpr) {
       case 1: {
         const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, cdiv(A->n_local, 256)));
         b2a::spmv_csr_scalar_kernel<DT><<<(unsigned)grid, 256, 0, ctx->stream>>>(
-            A->n_local, A->d_ptr, A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y, poison);
+            A->n_local, A->d_ptr, A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y, poison, xw.pv, xw.wait);
         break;
       }
-      case 2: launch_spmv_vec<DT, 2>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
-      case 4: launch_spmv_vec<DT, 4>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
-      case 8: launch_spmv_vec<DT, 8>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
-      case 16: launch_spmv_vec<DT, 16>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
-      default: launch_spmv_vec<DT, 32>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
+      case 2: launch_spmv_vec<DT, 2>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
+      case 4: launch_spmv_vec<DT, 4>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
+      case 8: launch_spmv_vec<DT, 8>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
+      case 16: launch_spmv_vec<DT, 16>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
+      default: launch_spmv_vec<DT, 32>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
     }
   }
   prof_end(ctx);
@@ -729,6 +770,7 @@ template <class HT>
 static int rotate(b2a_ws *ws, int col0, int K, int N, const HT *Qp, int move_src, int move_dst) {
   using DT = typename Dev<HT>::type;
   if (N <= 0 || K <= 0) return B2A_OK;
+  ws->x_pushed_col = -1;
   if (move_src == move_dst) move_src = move_dst = -1;
   CUDA_TRY(cudaMemcpyAsync(ws->dQ, Qp, (size_t)K * N * sizeof(HT), cudaMemcpyHostToDevice, ws->ctx->stream));
   bool ok = try_rotate<DT, 128>(ws, col0, K, N, move_src, move_dst);
@@ -840,6 +882,7 @@ static int iterate_arnoldi(b2a_ws *ws, b2a_op *A, int from, int to, uint64_t see
     if (!state.poison) break;
     // breakdown at step `last`: H[last+1, last] = 0 already; re-seed unless j == size(V,1)
     if (st) st->breakdowns += 1;
+    ws->x_pushed_col = -1;  // the broken step pushed nothing
     CUDA_TRY(cudaMemsetAsync(&ws->state->poison, 0, sizeof(int), ctx->stream));
     if ((int64_t)last != ws->n_global) {
       int ok_unused;
@@ -1041,6 +1084,8 @@ int b2a_ctx_create_dist(int device, int rank, int world, const void *nccl_unique
   return B2A_OK;
 }
 
+static void peer_release(b2a_ctx *ctx);
+
 int b2a_ctx_destroy(b2a_ctx *ctx) {
   if (!ctx) return B2A_OK;
   cudaSetDevice(ctx->device);
@@ -1049,6 +1094,7 @@ int b2a_ctx_destroy(b2a_ctx *ctx) {
     cudaEventDestroy(r.e1);
   }
   for (auto e : ctx->prof_pool) cudaEventDestroy(e);
+  peer_release(ctx);
   if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
   if (ctx->d_zero) cudaFree(ctx->d_zero);
   for (auto &pc : ctx->pinned_cache) cudaFreeHost(pc.second);
@@ -1407,15 +1453,169 @@ int b2a_op_bytes(b2a_op *op, double *bytes) {
 }
 
 // ------------------------------------------------------------------------- workspace
+static void peer_teardown(b2a_ws *ws);
+
 int b2a_ws_destroy(b2a_ws *ws) {
   if (!ws) return B2A_OK;
   cudaSetDevice(ws->ctx->device);
+  peer_teardown(ws);
   dev_free(ws->ctx, ws->dV);
   dev_free(ws->ctx, ws->arena);
   dev_free(ws->ctx, ws->xfull);
   pinned_put(ws->ctx, ws->pinned, ws->pinned_bytes);
   delete ws;
   return B2A_OK;
+}
+
+// Release the context's peer block (collective: all ranks call it at the same point).
+static void peer_release(b2a_ctx *ctx) {
+  if (!ctx->peer_local && ctx->peer_opened.empty()) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (void *p : ctx->peer_opened) cudaIpcCloseMemHandle(p);
+  ctx->peer_opened.clear();
+  if (ctx->world > 1 && ctx->comm) {
+    // exporters may only free after every importer has closed its mapping: a tiny all-reduce as barrier
+    double *dd = nullptr;
+    if (dev_alloc(ctx, reinterpret_cast<void **>(&dd), sizeof(double)) == cudaSuccess) {
+      cudaMemsetAsync(dd, 0, sizeof(double), ctx->stream);
+      g_nccl.AllReduce(dd, dd, 1, ncclFloat64, ncclSum, ctx->comm, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+      dev_free(ctx, dd);
+    }
+  }
+  if (ctx->peer_local) cudaFree(ctx->peer_local);
+  ctx->peer_local = nullptr;
+  ctx->peer_view = b2a::PeerView();
+  ctx->peer_slot = 0;
+  ctx->peer_x_bytes = 0;
+}
+
+// Give workspace `ws` the context's NVLink peer communication block, (re)creating it when it is too
+// small: allocate this rank's block, exchange CUDA IPC handles over the NCCL communicator and map every
+// peer's block.  Every decision is taken from values all ranks share, so the ranks stay in lockstep;
+// any failure leaves ws->peer.P == 1 (host-launched NCCL collectives are used instead).
+static int peer_setup(b2a_ctx *ctx, b2a_ws *ws) {
+  ws->peer = b2a::PeerView();
+  ws->peer_borrowed = false;
+  if (ctx->world < 2 || ctx->world > b2a::kPeerMaxRanks) return B2A_OK;
+  if (getenv("B2A_NO_PEER") && getenv("B2A_NO_PEER")[0] == '1') return B2A_OK;
+  if (ctx->peer_busy) return B2A_OK;  // one workspace at a time owns the block; others use NCCL
+  const int P = ctx->world;
+  const int slot = (ws->maxdim + 2) * 2 + 2;  // doubles: [h (complex worst case) | norm]
+  const size_t x_bytes = (size_t)ws->n_global * ws->esz + 64;
+  if (ctx->peer_view.P == P && ctx->peer_slot >= slot && ctx->peer_x_bytes >= x_bytes) {
+    ws->peer = ctx->peer_view;
+    ws->peer_borrowed = true;
+    ctx->peer_busy = true;
+    return B2A_OK;
+  }
+  peer_release(ctx);
+  size_t off = 0;
+  auto carve = [&](size_t bytes) {
+    const size_t at = off;
+    off += (bytes + 255) / 256 * 256;
+    return at;
+  };
+  const size_t o_hdr = carve(256);
+  const size_t o_flag_ar = carve(sizeof(unsigned long long) * b2a::kPeerBufs * P);
+  const size_t o_flag_x = carve(sizeof(unsigned long long) * P);
+  const size_t o_data = carve(sizeof(double) * b2a::kPeerBufs * P * slot);
+  const size_t o_x = carve(x_bytes);
+  const size_t total = off;
+  int okflag = 1;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ctx->peer_local), total);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    ctx->peer_local = nullptr;
+    okflag = 0;
+  } else {
+    cudaMemset(ctx->peer_local, 0, total);
+  }
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  if (okflag && cudaIpcGetMemHandle(&mine, ctx->peer_local) != cudaSuccess) {
+    (void)cudaGetLastError();
+    okflag = 0;
+  }
+  // exchange [okflag | handle] (padded to 128 bytes) with an NCCL all-gather
+  const size_t rec = 128;
+  std::vector<char> send(rec, 0), recv(rec * P, 0);
+  std::memcpy(send.data(), &okflag, sizeof(int));
+  std::memcpy(send.data() + 8, &mine, sizeof(mine));
+  char *d = nullptr;
+  CUDA_TRY(dev_alloc(ctx, reinterpret_cast<void **>(&d), rec * (P + 1)));
+  CUDA_TRY(cudaMemcpyAsync(d, send.data(), rec, cudaMemcpyHostToDevice, ctx->stream));
+  NCCL_TRY(g_nccl.AllGather(d, d + rec, rec, ncclChar, ctx->comm, ctx->stream));
+  CUDA_TRY(cudaMemcpyAsync(recv.data(), d + rec, rec * P, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  dev_free(ctx, d);
+  bool all_ok = true;
+  for (int r = 0; r < P; ++r) {
+    int f;
+    std::memcpy(&f, recv.data() + rec * r, sizeof(int));
+    all_ok = all_ok && f == 1;
+  }
+  int opened_ok = all_ok ? 1 : 0;
+  b2a::PeerView pv;
+  if (all_ok) {
+    for (int r = 0; r < P; ++r) {
+      if (r == ctx->rank) {
+        pv.peer[r] = ctx->peer_local;
+        continue;
+      }
+      cudaIpcMemHandle_t h;
+      std::memcpy(&h, recv.data() + rec * r + 8, sizeof(h));
+      void *ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        (void)cudaGetLastError();
+        opened_ok = 0;
+        break;
+      }
+      ctx->peer_opened.push_back(ptr);
+      pv.peer[r] = reinterpret_cast<char *>(ptr);
+    }
+  }
+  {  // second agreement round: did everybody manage to map everybody?
+    double *dd = nullptr;
+    CUDA_TRY(dev_alloc(ctx, reinterpret_cast<void **>(&dd), sizeof(double)));
+    const double v = opened_ok ? 0.0 : 1.0;
+    CUDA_TRY(cudaMemcpyAsync(dd, &v, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_TRY(g_nccl.AllReduce(dd, dd, 1, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
+    double tot = 1.0;
+    CUDA_TRY(cudaMemcpyAsync(&tot, dd, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, dd);
+    if (tot != 0.0) {
+      peer_release(ctx);
+      return B2A_OK;  // somebody failed: everyone keeps NCCL
+    }
+  }
+  pv.P = P;
+  pv.rank = ctx->rank;
+  pv.slot = slot;
+  pv.off_flag_ar = o_flag_ar;
+  pv.off_data_ar = o_data;
+  pv.off_flag_x = o_flag_x;
+  pv.off_x = o_x;
+  pv.seq_ar = reinterpret_cast<unsigned long long *>(ctx->peer_local + o_hdr);
+  pv.seq_x = pv.seq_ar + 1;
+  pv.err = reinterpret_cast<int *>(pv.seq_ar + 2);
+  ctx->peer_view = pv;
+  ctx->peer_slot = slot;
+  ctx->peer_x_bytes = x_bytes;
+  ws->peer = pv;
+  ws->peer_borrowed = true;
+  ctx->peer_busy = true;
+  return B2A_OK;
+}
+
+static void peer_teardown(b2a_ws *ws) {
+  if (ws->peer_borrowed) {
+    cudaStreamSynchronize(ws->ctx->stream);
+    ws->ctx->peer_busy = false;  // the block stays mapped in the context for the next workspace
+  }
+  ws->peer_borrowed = false;
+  ws->peer = b2a::PeerView();
 }
 
 static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_global, int64_t row_offset, int maxdim,
@@ -1464,6 +1664,7 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
   if (const char *e = getenv("B2A_TMA_RT_DOTS")) ws->tune_rt_dots = atoi(e);
   if (const char *e = getenv("B2A_TMA_RT_UPD")) ws->tune_rt_upd = atoi(e);
   if (const char *e = getenv("B2A_TMA_STAGES")) ws->tune_stages = atoi(e);
+  if (const char *e = getenv("B2A_FINISH_GRID")) ws->finish_grid_mult = std::max(1, atoi(e));
   CUDA_TRY(dev_alloc(ctx, &ws->dV, (size_t)ws->ld * m1 * es));
   CUDA_TRY(cudaMemsetAsync(ws->dV, 0, (size_t)ws->ld * m1 * es, ctx->stream));  // padding rows stay zero forever
   ws->H.assign((size_t)m1 * maxdim * es, 0);
@@ -1498,12 +1699,13 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
   ws->partials2 = reinterpret_cast<double *>(base + o_part2);
   ws->state = reinterpret_cast<b2a::SweepState *>(base + o_state);
   ws->dQ = base + o_dQ;
-  if (ctx->world > 1) {
+  const size_t want = (size_t)m1 * maxdim * es + sizeof(int) * (m1 + 1) + sizeof(b2a::SweepState) + 64;
+  CUDA_TRY(pinned_get(ctx, want, &ws->pinned, &ws->pinned_bytes));
+  B2A_TRY(peer_setup(ctx, ws));
+  if (ctx->world > 1 && ws->peer.P == 1) {  // NCCL fallback needs its own gather buffer
     const int64_t nx = ws->uniform_partition ? ws->all_counts[0] * ctx->world : n_global;
     CUDA_TRY(dev_alloc(ctx, &ws->xfull, (size_t)nx * es));
   }
-  const size_t want = (size_t)m1 * maxdim * es + sizeof(int) * (m1 + 1) + sizeof(b2a::SweepState) + 64;
-  CUDA_TRY(pinned_get(ctx, want, &ws->pinned, &ws->pinned_bytes));
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   return B2A_OK;
 }
@@ -1534,6 +1736,7 @@ int b2a_ws_set_col(b2a_ws *ws, int j, const void *host) {
   WS_COL_CHECK(ws, j);
   if (!host) return fail(B2A_ERR_ARGUMENT, "NULL host pointer");
   char *dst = reinterpret_cast<char *>(ws->dV) + (size_t)(j - 1) * ws->ld * ws->esz;
+  ws->x_pushed_col = -1;
   CUDA_TRY(cudaMemcpyAsync(dst, host, (size_t)ws->n_local * ws->esz, cudaMemcpyHostToDevice, ws->ctx->stream));
   CUDA_TRY(cudaStreamSynchronize(ws->ctx->stream));
   return B2A_OK;
@@ -1542,6 +1745,7 @@ int b2a_ws_set_col_device(b2a_ws *ws, int j, const void *dev) {
   WS_COL_CHECK(ws, j);
   if (!dev) return fail(B2A_ERR_ARGUMENT, "NULL device pointer");
   char *dst = reinterpret_cast<char *>(ws->dV) + (size_t)(j - 1) * ws->ld * ws->esz;
+  ws->x_pushed_col = -1;
   CUDA_TRY(cudaMemcpyAsync(dst, dev, (size_t)ws->n_local * ws->esz, cudaMemcpyDeviceToDevice, ws->ctx->stream));
   return B2A_OK;
 }

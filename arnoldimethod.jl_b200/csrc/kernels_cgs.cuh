@@ -19,6 +19,7 @@
 #pragma once
 
 #include "device_common.cuh"
+#include "peer_comm.cuh"
 
 namespace b2a {
 
@@ -234,7 +235,8 @@ template <class T>
 __global__ void __launch_bounds__(256)
     cgs_finish_kernel(T *__restrict__ v, int64_t n, int j, const T *__restrict__ h1, const T *__restrict__ h2,
                       const double *rsq_p, const double *w1sq_p, const double *w2sq_p, T *__restrict__ Hcol,
-                      int *info_col, SweepState *state, int step, int mode) {
+                      int *info_col, SweepState *state, int step, int mode, const __grid_constant__ PeerView pv,
+                      int64_t row_offset, int push) {
   if (state->poison) return;
   constexpr int PV = Scalar<T>::per_vec;
   double rnorm = sqrt(*rsq_p);
@@ -273,11 +275,79 @@ __global__ void __launch_bounds__(256)
   }
   const int64_t nvec = (n + PV - 1) / PV;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t iv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += stride) {
-    double2 x = *reinterpret_cast<const double2 *>(v + iv * PV);
-    x.x /= wnorm;  // v ./= wnorm (expansion.jl:106): a true division, like the reference
-    x.y /= wnorm;
-    *reinterpret_cast<double2 *>(v + iv * PV) = x;
+  const bool do_push = push && pv.P > 1;
+  const bool vec_ok = PV == 1 || (row_offset & 1) == 0;
+  constexpr int U = 4;  // vectors in flight per thread
+  for (int64_t iv0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; iv0 < nvec; iv0 += stride * U) {
+    double2 x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t iv = iv0 + u * stride;
+      x[u] = iv < nvec ? *reinterpret_cast<const double2 *>(v + iv * PV) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      x[u].x /= wnorm;  // v ./= wnorm (expansion.jl:106): a true division, like the reference
+      x[u].y /= wnorm;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t iv = iv0 + u * stride;
+      if (iv < nvec) *reinterpret_cast<double2 *>(v + iv * PV) = x[u];
+    }
+    if (do_push) {
+      // fused x-exchange: this rank's slice of the next mat-vec input goes straight into every
+      // rank's x buffer over NVLink (one 16-byte store per lane when the row offset allows it)
+      for (int p = 0; p < pv.P; ++p) {
+        T *pxb = reinterpret_cast<T *>(pv.peer[p] + pv.off_x) + row_offset;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t iv = iv0 + u * stride;
+          if (iv >= nvec) continue;
+          const int64_t r = iv * PV;
+          if (vec_ok && (PV == 1 || r + 1 < n)) {
+            *reinterpret_cast<double2 *>(pxb + r) = x[u];
+          } else {
+            reinterpret_cast<double *>(pxb + r)[0] = x[u].x;
+            if (r + 1 < n) reinterpret_cast<double *>(pxb + r)[1] = x[u].y;
+          }
+        }
+      }
+    }
+  }
+  if (do_push) {
+    __shared__ int last_cta;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last_cta = (atomicAdd(&state->ticket[5], 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (last_cta && threadIdx.x == 0) {
+      state->ticket[5] = 0u;
+      peer_x_publish(pv);
+    }
+  }
+}
+
+// Explicit push of a column that no fused finish kernel produced (start of a sweep, after a
+// rotation / re-seed / set_col).
+template <class T>
+__global__ void __launch_bounds__(256)
+    xpush_kernel(const T *__restrict__ v, int64_t n, SweepState *state, const __grid_constant__ PeerView pv,
+                 int64_t row_offset) {
+  if (state->poison) return;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
+    const T x = v[r];
+    for (int p = 0; p < pv.P; ++p) (reinterpret_cast<T *>(pv.peer[p] + pv.off_x) + row_offset)[r] = x;
+  }
+  __shared__ int last_cta;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last_cta = (atomicAdd(&state->ticket[5], 1u) == gridDim.x - 1u);
+  __syncthreads();
+  if (last_cta && threadIdx.x == 0) {
+    state->ticket[5] = 0u;
+    peer_x_publish(pv);
   }
 }
 

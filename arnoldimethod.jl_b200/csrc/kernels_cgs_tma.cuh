@@ -31,6 +31,7 @@
 
 #include "device_common.cuh"
 #include "kernels_cgs.cuh"
+#include "peer_comm.cuh"
 
 namespace b2a {
 
@@ -145,7 +146,7 @@ __device__ __forceinline__ void tile_dots(const T *tile, const T *xt, int RT, in
 template <class T, int CPW>
 __device__ __forceinline__ void publish_and_reduce(T (&acc)[CPW], double nacc, bool have_cols, bool have_norm, int ncols,
                                                    int warp, int lane, T *partials, T *hout, double *nrm2_out,
-                                                   unsigned int *ticket, int *is_last_smem) {
+                                                   unsigned int *ticket, int *is_last_smem, const PeerView &pv) {
   const int grid = gridDim.x;
   if (warp < kTmaConsumerWarps) {
     if (have_cols) {
@@ -186,6 +187,15 @@ __device__ __forceinline__ void publish_and_reduce(T (&acc)[CPW], double nacc, b
     }
   }
   if (threadIdx.x == 0) *ticket = 0u;
+  if (pv.P > 1) {
+    // fused cross-GPU all-reduce of [h | nrm2] (contiguous by construction) over NVLink peer memory
+    __syncthreads();
+    if (warp == 0) {
+      double *vals = have_cols ? reinterpret_cast<double *>(hout) : nrm2_out;
+      const int cnt = (have_cols ? ncols * (int)(sizeof(T) / sizeof(double)) : 0) + (have_norm && nrm2_out ? 1 : 0);
+      if (vals && cnt > 0) peer_allreduce_warp(pv, vals, cnt);
+    }
+  }
 }
 
 struct TmaSmem {
@@ -203,7 +213,8 @@ template <class T, int CPW>
 __global__ void __launch_bounds__(kTmaThreads, 1)
     cgs_dots_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ncols, TmaGeom g,
                         T *__restrict__ partials, T *__restrict__ hout, double *__restrict__ nrm2_out,
-                        unsigned int *ticket, const int *poison, const double *gate_rsq, const double *gate_w1sq) {
+                        unsigned int *ticket, const int *poison, const double *gate_rsq, const double *gate_w1sq,
+                        const __grid_constant__ PeerView pv) {
   if (*poison) return;
   if (gate_rsq && !dgks_fired(gate_rsq, gate_w1sq)) return;
 
@@ -241,7 +252,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       if (lane == 0) mbar_arrive(&sm->empty[s]);
     }
   }
-  publish_and_reduce<T, CPW>(acc, nacc, true, true, ncols, warp, lane, partials, hout, nrm2_out, ticket, &sm->is_last);
+  publish_and_reduce<T, CPW>(acc, nacc, true, true, ncols, warp, lane, partials, hout, nrm2_out, ticket, &sm->is_last, pv);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -255,7 +266,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     cgs_update_tma_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ v, int ncols, TmaGeom g,
                           const T *__restrict__ h, T *__restrict__ partials, T *__restrict__ cout,
                           double *__restrict__ nrm2_out, unsigned int *ticket, const int *poison,
-                          const double *gate_rsq, const double *gate_w1sq) {
+                          const double *gate_rsq, const double *gate_w1sq, const __grid_constant__ PeerView pv) {
   if (*poison) return;
   if (gate_rsq && !dgks_fired(gate_rsq, gate_w1sq)) return;
 
@@ -327,7 +338,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       }
     }
   }
-  publish_and_reduce<T, CPW>(acc, nacc, SPEC, true, ncols, warp, lane, partials, cout, nrm2_out, ticket, &sm->is_last);
+  publish_and_reduce<T, CPW>(acc, nacc, SPEC, true, ncols, warp, lane, partials, cout, nrm2_out, ticket, &sm->is_last, pv);
 }
 
 }  // namespace b2a

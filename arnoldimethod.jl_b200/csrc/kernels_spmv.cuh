@@ -15,6 +15,7 @@
 #pragma once
 
 #include "device_common.cuh"
+#include "peer_comm.cuh"
 
 namespace b2a {
 
@@ -32,8 +33,12 @@ template <class T, int LPR, int U>
 __global__ void __launch_bounds__(256)
     spmv_csr_vector_kernel(int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
                            const T *__restrict__ vals, const T *__restrict__ x, T *__restrict__ y,
-                           const int *poison) {
+                           const int *poison, const __grid_constant__ PeerView pv, int wait_x) {
   if (*poison) return;
+  if (wait_x) {  // multi-GPU: x is pushed by the peers (peer_comm.cuh); wait until every slice has landed
+    if (threadIdx.x == 0) peer_x_wait(pv);
+    __syncthreads();
+  }
   const int sub = threadIdx.x & (LPR - 1);
   const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / LPR;
@@ -97,8 +102,12 @@ template <class T>
 __global__ void __launch_bounds__(256)
     spmv_csr_scalar_kernel(int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
                            const T *__restrict__ vals, const T *__restrict__ x, T *__restrict__ y,
-                           const int *poison) {
+                           const int *poison, const __grid_constant__ PeerView pv, int wait_x) {
   if (*poison) return;
+  if (wait_x) {
+    if (threadIdx.x == 0) peer_x_wait(pv);
+    __syncthreads();
+  }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
     const int64_t s = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);

@@ -1,0 +1,124 @@
+// peer_comm.cuh - one-shot collectives over NVLink peer memory, callable from inside a kernel.
+//
+// Row-sharded Arnoldi needs, per orthogonalisation sweep, an all-reduce of the (j+1)-vector
+// [h | ||v||^2].  These are <= ~1 KB and purely latency-bound; a host-launched
+// ncclAllReduce costs 10-25 us each.  Instead, the CTA that finishes a reduction kernel last
+// performs the all-reduce itself before the kernel ends:
+//
+//   every rank owns a communication block (cudaMalloc + CUDA IPC, mapped into every peer process)
+//       data [kPeerBufs][P][slot] doubles,  flag [kPeerBufs][P] u64
+//   rank r:  for all peers p:  p.data[buf][r][:] = my partial     (plain stores over NVLink)
+//            __threadfence_system();  p.flag[buf][r] = seq         (st.release.sys)
+//            wait until my.flag[buf][p] == seq for every p          (ld.acquire.sys)
+//            result[i] = sum_p my.data[buf][p][i]  in rank order    => identical bits on every rank
+//
+// `seq` is a DEVICE counter that advances only when a collective really executes, so kernels that
+// gate themselves off (second Gram-Schmidt pass, poisoned sweep) stay consistent across ranks: all
+// ranks gate on the same all-reduced scalars.  kPeerBufs rotating buffers: a rank can be at most one
+// collective ahead of a peer that is still reading the previous one.
+#pragma once
+
+#include <stdint.h>
+
+namespace b2a {
+
+constexpr int kPeerBufs = 4;
+constexpr int kPeerMaxRanks = 16;
+constexpr unsigned long long kPeerSpinLimit = 1ull << 31;  // ~seconds; then flag an error instead of hanging
+
+struct PeerView {
+  int P = 1, rank = 0;
+  int slot = 0;                         // doubles per rank slot
+  char *peer[kPeerMaxRanks] = {nullptr};  // base of every rank's communication block (peer[rank] = local)
+  unsigned long long off_flag_ar = 0, off_data_ar = 0, off_flag_x = 0, off_x = 0;
+  unsigned long long *seq_ar = nullptr;  // local device counters
+  unsigned long long *seq_x = nullptr;
+  int *err = nullptr;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double *p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// In-place all-reduce (sum) of vals[0..cnt) across the P ranks.  Call with ONE full warp; vals is
+// local global memory already visible to the calling warp.
+__device__ __forceinline__ void peer_allreduce_warp(const PeerView &pv, double *vals, int cnt) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long seq = 0;
+  if (lane == 0) {
+    seq = *pv.seq_ar + 1ull;
+    *pv.seq_ar = seq;
+  }
+  seq = __shfl_sync(0xffffffffu, seq, 0);
+  const int buf = (int)(seq % kPeerBufs);
+  // 1. scatter my partial into every rank's block (my own included)
+  for (int p = 0; p < pv.P; ++p) {
+    double *dst = reinterpret_cast<double *>(pv.peer[p] + pv.off_data_ar) + ((size_t)buf * pv.P + pv.rank) * pv.slot;
+    for (int i = lane; i < cnt; i += 32) dst[i] = vals[i];
+  }
+  __threadfence_system();
+  __syncwarp();
+  // 2. publish
+  for (int p = lane; p < pv.P; p += 32) {
+    unsigned long long *f = reinterpret_cast<unsigned long long *>(pv.peer[p] + pv.off_flag_ar) + (size_t)buf * pv.P + pv.rank;
+    st_release_sys(f, seq);
+  }
+  // 3. wait for every rank's contribution
+  const unsigned long long *myf = reinterpret_cast<const unsigned long long *>(pv.peer[pv.rank] + pv.off_flag_ar) + (size_t)buf * pv.P;
+  for (int p = lane; p < pv.P; p += 32) {
+    unsigned long long spins = 0;
+    while (ld_acquire_sys(myf + p) != seq) {
+      if (++spins > kPeerSpinLimit) {
+        *pv.err = 1;
+        break;
+      }
+    }
+  }
+  __syncwarp();
+  // 4. sum in rank order
+  const double *myd = reinterpret_cast<const double *>(pv.peer[pv.rank] + pv.off_data_ar) + (size_t)buf * pv.P * pv.slot;
+  for (int i = lane; i < cnt; i += 32) {
+    double s = 0.0;
+    for (int p = 0; p < pv.P; ++p) s += ld_relaxed_sys_f64(myd + (size_t)p * pv.slot + i);
+    vals[i] = s;
+  }
+  __syncwarp();
+}
+
+// ---- x exchange: push model ----------------------------------------------------------------
+// The kernel that produces this rank's slice of the next mat-vec input stores it into EVERY rank's
+// x buffer (peer[p] + off_x, indexed by global row).  Each CTA fences its remote stores; the CTA that
+// finishes last bumps the device counter seq_x and publishes it in every peer's flag_x[rank].
+// The consumer (SpMV) waits until all P flags reached its own seq_x.
+__device__ __forceinline__ void peer_x_publish(const PeerView &pv) {  // one thread of the last CTA
+  const unsigned long long seq = *pv.seq_x + 1ull;
+  *pv.seq_x = seq;
+  __threadfence_system();
+  for (int p = 0; p < pv.P; ++p)
+    st_release_sys(reinterpret_cast<unsigned long long *>(pv.peer[p] + pv.off_flag_x) + pv.rank, seq);
+}
+__device__ __forceinline__ void peer_x_wait(const PeerView &pv) {  // one thread per CTA, then __syncthreads
+  const unsigned long long want = *reinterpret_cast<volatile unsigned long long *>(pv.seq_x);
+  const unsigned long long *f = reinterpret_cast<const unsigned long long *>(pv.peer[pv.rank] + pv.off_flag_x);
+  for (int p = 0; p < pv.P; ++p) {
+    unsigned long long spins = 0;
+    while (ld_acquire_sys(f + p) < want) {
+      if (++spins > kPeerSpinLimit) {
+        *pv.err = 2;
+        break;
+      }
+    }
+  }
+}
+
+}  // namespace b2a
