@@ -99,6 +99,11 @@ SIGNATURES = {
     "b2a_rotate_final": (_i, [_vp, _i, _vp, _i, C.POINTER(Stats)]),
     "b2a_basis_times": (_i, [_vp, _i, _vp, _i, _vp, _i64]),
     "b2a_ws_matvec": (_i, [_vp, _vp, _i, _i]),
+    "b2a_ws_nrm2": (_i, [_vp, _i, _pd]),
+    "b2a_ws_gemv_c": (_i, [_vp, _i, _i, _vp]),
+    "b2a_ws_gemv_n_sub": (_i, [_vp, _i, _i, _vp]),
+    "b2a_ws_scal_div": (_i, [_vp, _i, _d]),
+    "b2a_ws_copy_col": (_i, [_vp, _i, _i]),
     "b2a_partialschur": (_i, [_vp, _vp, C.POINTER(Params), C.POINTER(HistoryC), _vp]),
     "b2a_host_local_schurfact": (_i, [_i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i]),
     "b2a_host_restart": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _d, _i, _i, _pi, _pi, _pi, _vp, _vp]),

@@ -373,6 +373,35 @@ class ArnoldiWorkspace:
             L.check(L.lib().b2a_rotate_final(self._h, int(nconv), _ptr(Qf), Qf.shape[0], C.byref(st)))
         return st
 
+    # -- BLAS-level operations of the reference's generic code (slow path: one call each)
+    def norm(self, j):
+        """``norm(view(V, :, j))``"""
+        r = C.c_double()
+        L.check(L.lib().b2a_ws_nrm2(self._h, int(j), C.byref(r)))
+        return r.value
+
+    def gemv_c(self, ncols, j):
+        """``view(V, :, 1:ncols)' * view(V, :, j)``"""
+        h = np.zeros(ncols, dtype=self.dtype)
+        if ncols:
+            L.check(L.lib().b2a_ws_gemv_c(self._h, int(ncols), int(j), _ptr(h)))
+        return h
+
+    def gemv_n_sub(self, ncols, j, h):
+        """``mul!(view(V, :, j), view(V, :, 1:ncols), h, -1, 1)``"""
+        h = np.ascontiguousarray(h, dtype=self.dtype)
+        assert h.shape == (ncols,)
+        if ncols:
+            L.check(L.lib().b2a_ws_gemv_n_sub(self._h, int(ncols), int(j), _ptr(h)))
+
+    def scal_div(self, j, alpha):
+        """``view(V, :, j) ./= alpha``"""
+        L.check(L.lib().b2a_ws_scal_div(self._h, int(j), float(alpha)))
+
+    def copy_col(self, jsrc, jdst):
+        """``copyto!(view(V, :, jdst), view(V, :, jsrc))``"""
+        L.check(L.lib().b2a_ws_copy_col(self._h, int(jsrc), int(jdst)))
+
     def basis_times(self, Y):
         """``V[:, 1:nconv] * Y`` for a small complex Y (partialeigen)."""
         Y = np.asfortranarray(Y, dtype=np.complex128)

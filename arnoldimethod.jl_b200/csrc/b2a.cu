@@ -355,7 +355,7 @@ static int launch_update(b2a_ws *ws, int ncols, DT *v, const DT *h, double *nrm2
   const int64_t nvec = cdiv(ws->n_local, PV);
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(ws->upd_grid_max, cdiv(nvec, b2a::kCgsThreads)));
   prof_begin(ws->ctx, B2A_K_UPDATE, (double)(ncols + 2) * ws->n_local * sizeof(DT), gate_step);
-  b2a::cgs_update_kernel<DT><<<(unsigned)grid, b2a::kCgsThreads, ncols * sizeof(DT), ws->ctx->stream>>>(
+  b2a::cgs_update_kernel<DT><<<(unsigned)grid, b2a::kCgsThreads, (ncols + 8) * sizeof(DT), ws->ctx->stream>>>(
       col<DT>(ws, 0), ws->ld, v, ws->n_local, ncols, h, ws->partials2, nrm2, &ws->state->ticket[1],
       &ws->state->poison, g_rsq, g_w1sq);
   prof_end(ws->ctx);
@@ -1915,6 +1915,107 @@ int b2a_basis_times(b2a_ws *ws, int nconv, const double *Y, int ldy, double *X, 
   dev_free(ctx, dY);
   dev_free(ctx, dX);
   CUDA_TRY(e);
+  return B2A_OK;
+}
+
+// --------------------------------------------------------- fine-grained vector operations
+extern "C++" {
+// dots of column j0 (0-based) against columns [0, ncols): result in ws->hb1 = [h | ||v||^2], all-reduced
+template <class DT> static int fine_dots(b2a_ws *ws, int ncols, int j0) {
+  b2a_ctx *ctx = ws->ctx;
+  DT *v = eng::col<DT>(ws, j0);
+  DT *h1 = reinterpret_cast<DT *>(ws->hb1);
+  double *rsq = reinterpret_cast<double *>(h1 + ncols);
+  // the TMA kernels expect v to be column `ncols` of the panel; use them only in that layout
+  const bool tma = (j0 == ncols) && eng::tma_path_ok(ws, ncols, sizeof(DT));
+  if (tma) {
+    B2A_TRY(eng::launch_dots_tma<DT>(ws, ncols, v, h1, rsq, nullptr, nullptr, 0, false));
+    if (ws->peer.P == 1) B2A_TRY(eng::allreduce_f64(ctx, h1, (size_t)ncols * sizeof(DT) / 8 + 1));
+  } else {
+    B2A_TRY(eng::launch_dots<DT>(ws, ncols, v, h1, rsq, nullptr, nullptr));
+    B2A_TRY(eng::allreduce_f64(ctx, h1, (size_t)ncols * sizeof(DT) / 8 + 1));
+  }
+  return B2A_OK;
+}
+template <class DT> static int fine_nrm2(b2a_ws *ws, int j0, double *result) {
+  B2A_TRY(fine_dots<DT>(ws, 0, j0));
+  CUDA_TRY(cudaMemcpyAsync(ws->pinned, ws->hb1, sizeof(double), cudaMemcpyDeviceToHost, ws->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ws->ctx->stream));
+  prof_collect(ws->ctx, nullptr, 0, 0);
+  double sq;
+  std::memcpy(&sq, ws->pinned, sizeof(double));
+  *result = std::sqrt(sq);
+  return B2A_OK;
+}
+template <class DT> static int fine_gemv_c(b2a_ws *ws, int ncols, int j0, void *h_host) {
+  B2A_TRY(fine_dots<DT>(ws, ncols, j0));
+  CUDA_TRY(cudaMemcpyAsync(ws->pinned, ws->hb1, (size_t)ncols * sizeof(DT), cudaMemcpyDeviceToHost, ws->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ws->ctx->stream));
+  prof_collect(ws->ctx, nullptr, 0, 0);
+  std::memcpy(h_host, ws->pinned, (size_t)ncols * sizeof(DT));
+  return B2A_OK;
+}
+template <class DT> static int fine_gemv_n_sub(b2a_ws *ws, int ncols, int j0, const void *h_host) {
+  b2a_ctx *ctx = ws->ctx;
+  DT *h2 = reinterpret_cast<DT *>(ws->hb2);
+  std::memcpy(ws->pinned, h_host, (size_t)ncols * sizeof(DT));
+  CUDA_TRY(cudaMemcpyAsync(h2, ws->pinned, (size_t)ncols * sizeof(DT), cudaMemcpyHostToDevice, ctx->stream));
+  // LDG kernel: its norm output is not needed here (no collective)
+  B2A_TRY(eng::launch_update<DT>(ws, ncols, eng::col<DT>(ws, j0), h2, ws->w2sq, nullptr, nullptr));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  prof_collect(ctx, nullptr, 0, 0);
+  ws->x_pushed_col = -1;
+  return B2A_OK;
+}
+}  // extern "C++"
+
+#define FINE_CHECK(ws, j) \
+  ARG_CHECK((ws) && (j) >= 1 && (j) <= (ws)->maxdim + 1, "column index out of range")
+
+int b2a_ws_nrm2(b2a_ws *ws, int j, double *result) {
+  FINE_CHECK(ws, j);
+  if (!result) return fail(B2A_ERR_ARGUMENT, "NULL result");
+  CUDA_TRY(cudaSetDevice(ws->ctx->device));
+  return ws->dtype == B2A_F64 ? fine_nrm2<double>(ws, j - 1, result) : fine_nrm2<cdouble>(ws, j - 1, result);
+}
+int b2a_ws_gemv_c(b2a_ws *ws, int ncols, int j, void *h_host) {
+  FINE_CHECK(ws, j);
+  ARG_CHECK(ncols >= 0 && ncols <= ws->maxdim + 1 && h_host, "bad panel width");
+  if (ncols == 0) return B2A_OK;
+  CUDA_TRY(cudaSetDevice(ws->ctx->device));
+  return ws->dtype == B2A_F64 ? fine_gemv_c<double>(ws, ncols, j - 1, h_host) : fine_gemv_c<cdouble>(ws, ncols, j - 1, h_host);
+}
+int b2a_ws_gemv_n_sub(b2a_ws *ws, int ncols, int j, const void *h_host) {
+  FINE_CHECK(ws, j);
+  ARG_CHECK(ncols >= 0 && ncols <= ws->maxdim + 1 && h_host, "bad panel width");
+  ARG_CHECK(j > ncols, "the updated column must lie outside the panel");
+  if (ncols == 0) return B2A_OK;
+  CUDA_TRY(cudaSetDevice(ws->ctx->device));
+  return ws->dtype == B2A_F64 ? fine_gemv_n_sub<double>(ws, ncols, j - 1, h_host) : fine_gemv_n_sub<cdouble>(ws, ncols, j - 1, h_host);
+}
+int b2a_ws_scal_div(b2a_ws *ws, int j, double alpha) {
+  FINE_CHECK(ws, j);
+  b2a_ctx *ctx = ws->ctx;
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, cdiv(ws->n_local, 256)));
+  if (ws->dtype == B2A_F64)
+    b2a::scal_div_kernel<double><<<(unsigned)grid, 256, 0, ctx->stream>>>(eng::col<double>(ws, j - 1), ws->n_local, alpha);
+  else
+    b2a::scal_div_kernel<cdouble><<<(unsigned)grid, 256, 0, ctx->stream>>>(eng::col<cdouble>(ws, j - 1), ws->n_local, alpha);
+  ctx->launches++;
+  CUDA_TRY(cudaGetLastError());
+  ws->x_pushed_col = -1;
+  return B2A_OK;
+}
+int b2a_ws_copy_col(b2a_ws *ws, int jsrc, int jdst) {
+  FINE_CHECK(ws, jsrc);
+  FINE_CHECK(ws, jdst);
+  if (jsrc == jdst) return B2A_OK;
+  CUDA_TRY(cudaSetDevice(ws->ctx->device));
+  const char *src = reinterpret_cast<const char *>(ws->dV) + (size_t)(jsrc - 1) * ws->ld * ws->esz;
+  char *dst = reinterpret_cast<char *>(ws->dV) + (size_t)(jdst - 1) * ws->ld * ws->esz;
+  CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)ws->n_local * ws->esz, cudaMemcpyDeviceToDevice, ws->ctx->stream));
+  ws->x_pushed_col = -1;
   return B2A_OK;
 }
 

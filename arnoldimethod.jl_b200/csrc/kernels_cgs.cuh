@@ -328,6 +328,20 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// v ./= alpha (fine-grained API, b2a_ws_scal_div)
+template <class T>
+__global__ void __launch_bounds__(256) scal_div_kernel(T *__restrict__ v, int64_t n, double alpha) {
+  constexpr int PV = Scalar<T>::per_vec;
+  const int64_t nvec = (n + PV - 1) / PV;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t iv = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += stride) {
+    double2 x = *reinterpret_cast<const double2 *>(v + iv * PV);
+    x.x /= alpha;
+    x.y /= alpha;
+    *reinterpret_cast<double2 *>(v + iv * PV) = x;
+  }
+}
+
 // Explicit push of a column that no fused finish kernel produced (start of a sweep, after a
 // rotation / re-seed / set_col).
 template <class T>

@@ -207,6 +207,23 @@ int b2a_basis_times(b2a_ws *ws, int nconv, const double *Y_host_c64, int ldy, do
 /* single operator application y = A x on workspace columns: V[:, jdst] <- A V[:, jsrc] */
 int b2a_ws_matvec(b2a_ws *ws, b2a_op *A, int jsrc, int jdst);
 
+/* ---------------------------------------------------------- fine-grained vector operations
+ * The BLAS-level operations the reference's GENERIC code performs on V-typed objects
+ * (src/expansion.jl:17-57,70-107: norm, Vprev' * v, mul!(v, Vprev, h, -1, 1), v ./= a, copyto!), one
+ * entry point each, so that the unmodified generic methods can run on a device array type (slow path,
+ * one call + host round trip per operation; the fused sweeps above are the fast path).  Columns 1-based. */
+
+/* norm(view(V, :, j)) - global 2-norm (all-reduced when sharded) */
+int b2a_ws_nrm2(b2a_ws *ws, int j, double *result);
+/* h = view(V, :, 1:ncols)' * view(V, :, j)   (h_host: ncols entries of the workspace dtype) */
+int b2a_ws_gemv_c(b2a_ws *ws, int ncols, int j, void *h_host);
+/* mul!(view(V, :, j), view(V, :, 1:ncols), h, -1, 1):  V[:, j] -= V[:, 1:ncols] * h */
+int b2a_ws_gemv_n_sub(b2a_ws *ws, int ncols, int j, const void *h_host);
+/* view(V, :, j) ./= alpha (alpha real) */
+int b2a_ws_scal_div(b2a_ws *ws, int j, double alpha);
+/* copyto!(view(V, :, jdst), view(V, :, jsrc)) */
+int b2a_ws_copy_col(b2a_ws *ws, int jsrc, int jdst);
+
 /* ------------------------------------------------------------- whole restart loop
  * partialschur / partialschur! - src/run.jl:100-179 + _partialschur :224-392, with the
  * m x m algebra (src/schurfact.jl, src/schursort.jl, src/restore_hessenberg.jl,

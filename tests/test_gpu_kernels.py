@@ -348,3 +348,49 @@ def test_spmv_tma_stream_kernel_opt_in(ctx, monkeypatch):
         ws.matvec(op, 1, 2)
         y = ws.get_cols(2, 1)[:, 0]
         assert np.abs(y - A @ x).max() <= 64 * EPS * (abs(A) @ abs(x)).max()
+
+
+@pytest.mark.parametrize("T", TYPES)
+def test_generic_method_on_device_ops(ctx, T):
+    """The reference's GENERIC orthogonalize! (src/expansion.jl:69-109) executed operation by operation
+    through the BLAS-level entry points (norm, V'v, v -= V h, v ./= a) equals the fused device sweep."""
+    rng = np.random.default_rng(31)
+    n, j = 20003, 9
+    Vp = orthonormal_panel(rng, T, n, j)
+    for kind in ("generic", "nearly_dependent"):
+        v = randn(rng, T, n)
+        if kind == "nearly_dependent":
+            v = Vp @ randn(rng, T, j) + 1e-6 * v
+        ws1 = b2a.ArnoldiWorkspace(n, j + 1, dtype=T, ctx=ctx)
+        ws2 = b2a.ArnoldiWorkspace(n, j + 1, dtype=T, ctx=ctx)
+        for w in (ws1, ws2):
+            for c in range(j):
+                w.set_col(c + 1, Vp[:, c])
+            w.set_col(j + 1, v)
+        # generic method, one device call per BLAS operation
+        eta = np.sqrt(2) / 2
+        rnorm = ws1.norm(j + 1)
+        assert abs(rnorm - np.linalg.norm(v)) <= 1e-14 * rnorm
+        h = ws1.gemv_c(j, j + 1)
+        ws1.gemv_n_sub(j, j + 1, h)
+        wnorm = ws1.norm(j + 1)
+        second = wnorm < eta * rnorm
+        if second:
+            rnorm = wnorm
+            c = ws1.gemv_c(j, j + 1)
+            ws1.gemv_n_sub(j, j + 1, c)
+            h = h + c
+            wnorm = ws1.norm(j + 1)
+        assert wnorm > eta * rnorm
+        ws1.scal_div(j + 1, wnorm)
+        assert second == (kind == "nearly_dependent")
+        # fused sweep
+        assert ws2.orthogonalize(j)
+        tol = 1e-13 if kind == "generic" else 1e-9
+        assert relerr(ws2.H[:j, j - 1], h) <= 1e-13
+        assert abs(ws2.H[j, j - 1] - wnorm) <= tol * wnorm
+        assert np.linalg.norm(ws1.get_cols(j + 1, 1) - ws2.get_cols(j + 1, 1)) <= tol
+        ws1.copy_col(j + 1, 1)
+        assert np.array_equal(ws1.get_cols(1, 1), ws1.get_cols(j + 1, 1))
+        ws1.close()
+        ws2.close()
