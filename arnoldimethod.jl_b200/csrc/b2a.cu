@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "b200arnoldi.h"
@@ -273,7 +274,7 @@ struct b2a_ws {
   bool peer_borrowed = false;
   int finish_grid_mult = 4;
   int x_pushed_col = -1;  // 0-based column whose normalised content currently sits in every rank's x buffer
-  int tune_rt_dots = 0, tune_rt_upd = 0, tune_stages = 0, tune_grid_mult = 1;  // experiment overrides (env)
+  int tune_rt_dots = 0, tune_rt_upd = 0, tune_stages = 0, tune_ctas = 1, tune_l2promo = 2;  // experiment overrides (env)
 };
 
 template <class HT> struct Dev;
@@ -286,6 +287,24 @@ static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ======================================================================= device engine
 namespace eng {
+
+// Launch with the programmatic-stream-serialization attribute (PDL, see device_common.cuh).
+static bool g_pdl = !(getenv("B2A_PDL") && getenv("B2A_PDL")[0] == '0');
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                              Args &&...args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 template <class DT> static inline DT *col(b2a_ws *ws, int c0) {
   return reinterpret_cast<DT *>(ws->dV) + (int64_t)c0 * ws->ld;
@@ -400,7 +419,7 @@ static bool make_panel_tmap(const b2a_ws *ws, int ncols, int RT, CUtensorMap *tm
   cuuint32_t box[2] = {(cuuint32_t)(RT * inner), (cuuint32_t)(ncols + 1)};
   cuuint32_t estr[2] = {1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, ws->dV, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+             CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)ws->tune_l2promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
          CUDA_SUCCESS;
 }
 
@@ -409,6 +428,7 @@ static bool tma_geometry(const b2a_ws *ws, int ncols, size_t elem, bool update, 
                          size_t *smem_bytes, int *grid) {
   if (ncols > b2a::kTmaMaxCols) return false;
   const size_t header = 256 + (update ? b2a::kTmaMaxCols * elem : 0);
+  const size_t budget = kTmaSmemBudget / ws->tune_ctas - (ws->tune_ctas > 1 ? 2048 : 0);
   const size_t row_bytes = (size_t)(ncols + 1) * elem;
   const int min_rt = elem == 8 ? 64 : 32;
   const int max_rt = elem == 8 ? 256 : 128;  // tensor-map box: inner dimension <= 256 doubles
@@ -416,17 +436,17 @@ static bool tma_geometry(const b2a_ws *ws, int ncols, size_t elem, bool update, 
   // consumer warps own a 32-row slab in phase 1); never more rows than the vector has
   int RT = max_rt;
   while (RT > min_rt && (size_t)RT * row_bytes > 64 * 1024) RT >>= 1;
-  if (update && RT < 256 && max_rt >= 256 && 2 * 256 * row_bytes + header <= kTmaSmemBudget) RT = 256;
+  if (update && RT < 256 && max_rt >= 256 && 2 * 256 * row_bytes + header <= budget) RT = 256;
   const int forced = update ? ws->tune_rt_upd : ws->tune_rt_dots;
   if (forced >= min_rt && forced <= max_rt && (forced & (forced - 1)) == 0) RT = forced;
   while (RT > min_rt && (int64_t)RT / 2 >= ws->n_local) RT >>= 1;
   const size_t stage_bytes = (size_t)RT * row_bytes;
-  int stages = (int)std::min<size_t>(b2a::kTmaMaxStages, (kTmaSmemBudget - header) / stage_bytes);
+  int stages = (int)std::min<size_t>(b2a::kTmaMaxStages, (budget - header) / stage_bytes);
   if (ws->tune_stages >= 2) stages = std::min(stages, ws->tune_stages);
   if (stages < 2) return false;
   const int64_t ntiles = cdiv(std::max<int64_t>(ws->n_local, 1), RT);
   if (ntiles > 2000000000LL) return false;
-  int gr = (int)std::min<int64_t>(ws->ctx->num_sms, ntiles);
+  int gr = (int)std::min<int64_t>((int64_t)ws->ctx->num_sms * ws->tune_ctas, ntiles);
   const int tpc = (int)cdiv(ntiles, gr);
   gr = (int)cdiv(ntiles, tpc);
   stages = std::min(stages, std::max(2, tpc));
@@ -459,9 +479,9 @@ static int launch_dots_tma_inst(b2a_ws *ws, const DT *v, int ncols, const b2a::T
   if (!make_panel_tmap(ws, ncols, g.RT, &tm)) return fail(B2A_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   (void)v;  // v is column `ncols` of the tensor map
   prof_begin(ws->ctx, B2A_K_DOTS, (double)(ncols + 1) * ws->n_local * sizeof(DT), gate_step);
-  kern<<<grid, b2a::kTmaThreads, smem, ws->ctx->stream>>>(tm, ncols, g, reinterpret_cast<DT *>(ws->partials), hout,
-                                                            nrm2, &ws->state->ticket[2], &ws->state->poison, g_rsq,
-                                                            g_w1sq, ws->peer);
+  CUDA_TRY(launch_pdl(kern, (unsigned)grid, (unsigned)b2a::kTmaThreads, smem, ws->ctx->stream, tm, ncols, g,
+                      reinterpret_cast<DT *>(ws->partials), hout, nrm2, &ws->state->ticket[2],
+                      (const int *)&ws->state->poison, g_rsq, g_w1sq, ws->peer));
   prof_end(ws->ctx);
   ws->ctx->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -500,9 +520,9 @@ static int launch_update_tma_inst(b2a_ws *ws, DT *v, int ncols, const b2a::TmaGe
   CUtensorMap tm;
   if (!make_panel_tmap(ws, ncols, g.RT, &tm)) return fail(B2A_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   prof_begin(ws->ctx, B2A_K_UPDATE, (double)(ncols + 2) * ws->n_local * sizeof(DT), gate_step);
-  kern<<<grid, b2a::kTmaThreads, smem, ws->ctx->stream>>>(tm, v, ncols, g, h, reinterpret_cast<DT *>(ws->partials),
-                                                            cout, nrm2, &ws->state->ticket[3], &ws->state->poison,
-                                                            g_rsq, g_w1sq, ws->peer);
+  CUDA_TRY(launch_pdl(kern, (unsigned)grid, (unsigned)b2a::kTmaThreads, smem, ws->ctx->stream, tm, v, ncols, g, h,
+                      reinterpret_cast<DT *>(ws->partials), cout, nrm2, &ws->state->ticket[3],
+                      (const int *)&ws->state->poison, g_rsq, g_w1sq, ws->peer));
   prof_end(ws->ctx);
   ws->ctx->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -591,9 +611,10 @@ template <class DT> static int enqueue_cgs(b2a_ws *ws, int j, int mode, int step
   DT *Hcol = reinterpret_cast<DT *>(ws->dH) + (int64_t)(std::max(j, 1) - 1) * (ws->maxdim + 1);
   prof_begin(ctx, B2A_K_FINISH, 2.0 * ws->n_local * sizeof(DT));
   const int push = (mode == 0 && ws->peer.P > 1) ? 1 : 0;  // Arnoldi step: the new column is the next mat-vec input
-  b2a::cgs_finish_kernel<DT><<<(unsigned)grid, 256, 0, ctx->stream>>>(
-      v, ws->n_local, j, h1, h2, rsq, w1sq, ws->w2sq, Hcol, ws->dinfo + j, ws->state, step, mode, ws->peer,
-      ws->row_offset, push);
+  CUDA_TRY(launch_pdl(b2a::cgs_finish_kernel<DT>, (unsigned)grid, 256u, 0, ctx->stream, v, ws->n_local, j,
+                      (const DT *)h1, (const DT *)h2, (const double *)rsq, (const double *)w1sq,
+                      (const double *)ws->w2sq, Hcol, ws->dinfo + j, ws->state, step, mode, ws->peer, ws->row_offset,
+                      push));
   prof_end(ctx);
   ctx->launches++;
   ws->x_pushed_col = push ? j : -1;
@@ -613,8 +634,9 @@ static void launch_spmv_vec_u(b2a_op *A, const DT *x, DT *y, const int *poison, 
                               const XWait &xw) {
   const int64_t threads = cdiv(A->n_local, U) * LPR;
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * A->grid_mult, cdiv(threads, 256)));
-  b2a::spmv_csr_vector_kernel<DT, LPR, U><<<(unsigned)grid, 256, 0, st>>>(
-      A->n_local, A->d_ptr, A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y, poison, xw.pv, xw.wait);
+  (void)launch_pdl(b2a::spmv_csr_vector_kernel<DT, LPR, U>, (unsigned)grid, 256u, 0, st, A->n_local,
+                   (const int64_t *)A->d_ptr, (const int32_t *)A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y,
+                   poison, xw.pv, xw.wait);
 }
 template <class DT, int LPR>
 static void launch_spmv_vec(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms,
@@ -1665,6 +1687,8 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
   if (const char *e = getenv("B2A_TMA_RT_UPD")) ws->tune_rt_upd = atoi(e);
   if (const char *e = getenv("B2A_TMA_STAGES")) ws->tune_stages = atoi(e);
   if (const char *e = getenv("B2A_FINISH_GRID")) ws->finish_grid_mult = std::max(1, atoi(e));
+  if (const char *e = getenv("B2A_TMA_CTAS")) ws->tune_ctas = std::max(1, std::min(2, atoi(e)));
+  if (const char *e = getenv("B2A_TMA_L2PROMO")) ws->tune_l2promo = std::max(0, std::min(3, atoi(e)));
   CUDA_TRY(dev_alloc(ctx, &ws->dV, (size_t)ws->ld * m1 * es));
   CUDA_TRY(cudaMemsetAsync(ws->dV, 0, (size_t)ws->ld * m1 * es, ctx->stream));  // padding rows stay zero forever
   ws->H.assign((size_t)m1 * maxdim * es, 0);

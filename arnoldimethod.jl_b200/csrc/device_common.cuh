@@ -89,6 +89,13 @@ __device__ __forceinline__ double2 ldg_stream(const double2 *p) {
   return r;
 }
 
+// Programmatic dependent launch (PDL): kernels of a sweep are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the launch and prologue of kernel N+1 overlap
+// the tail of kernel N.  pdl_wait() must precede the first read of anything a predecessor wrote;
+// pdl_trigger() lets the successor's CTAs be scheduled as soon as SMs free up.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Device-side record of one Arnoldi / re-seed step.  All decisions of
 // src/expansion.jl:91,99 are taken on the device from these (all-reduced) scalars so
 // that a whole sweep can be enqueued without a host round trip.

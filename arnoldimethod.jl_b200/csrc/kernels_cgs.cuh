@@ -237,6 +237,7 @@ __global__ void __launch_bounds__(256)
                       const double *rsq_p, const double *w1sq_p, const double *w2sq_p, T *__restrict__ Hcol,
                       int *info_col, SweepState *state, int step, int mode, const __grid_constant__ PeerView pv,
                       int64_t row_offset, int push) {
+  pdl_wait();
   if (state->poison) return;
   constexpr int PV = Scalar<T>::per_vec;
   double rnorm = sqrt(*rsq_p);

@@ -210,19 +210,17 @@ struct TmaSmem {
 // S1: h[c] = sum_r conj(V[r,c]) v[r], nrm2 = ||v||^2
 // ---------------------------------------------------------------------------------------
 template <class T, int CPW>
-__global__ void __launch_bounds__(kTmaThreads, 1)
+__global__ void __launch_bounds__(kTmaThreads, 2)
     cgs_dots_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ncols, TmaGeom g,
                         T *__restrict__ partials, T *__restrict__ hout, double *__restrict__ nrm2_out,
                         unsigned int *ticket, const int *poison, const double *gate_rsq, const double *gate_w1sq,
                         const __grid_constant__ PeerView pv) {
-  if (*poison) return;
-  if (gate_rsq && !dgks_fired(gate_rsq, gate_w1sq)) return;
-
   extern __shared__ __align__(128) unsigned char tma_smem_raw[];
   TmaSmem *sm = reinterpret_cast<TmaSmem *>(tma_smem_raw);
   T *ring = reinterpret_cast<T *>(tma_smem_raw + 256);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  // prologue that does not depend on the previous kernel: overlaps its tail under PDL
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap);
     for (int s = 0; s < g.stages; ++s) {
@@ -231,6 +229,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     }
     mbar_fence_init();
   }
+  pdl_wait();
+  if (*poison) return;
+  if (gate_rsq && !dgks_fired(gate_rsq, gate_w1sq)) return;
   __syncthreads();
 
   T acc[CPW];
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       if (lane == 0) mbar_arrive(&sm->empty[s]);
     }
   }
+  pdl_trigger();  // main loop done: let the next kernel's launch overlap the final reduction
   publish_and_reduce<T, CPW>(acc, nacc, true, true, ncols, warp, lane, partials, hout, nrm2_out, ticket, &sm->is_last, pv);
 }
 
@@ -262,14 +264,11 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
 //          stage.  Phase 2 (SPEC): the warp-owns-columns dot of S1 on the updated tile.
 // ---------------------------------------------------------------------------------------
 template <class T, int CPW, bool SPEC>
-__global__ void __launch_bounds__(kTmaThreads, 1)
+__global__ void __launch_bounds__(kTmaThreads, 2)
     cgs_update_tma_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ v, int ncols, TmaGeom g,
                           const T *__restrict__ h, T *__restrict__ partials, T *__restrict__ cout,
                           double *__restrict__ nrm2_out, unsigned int *ticket, const int *poison,
                           const double *gate_rsq, const double *gate_w1sq, const __grid_constant__ PeerView pv) {
-  if (*poison) return;
-  if (gate_rsq && !dgks_fired(gate_rsq, gate_w1sq)) return;
-
   extern __shared__ __align__(128) unsigned char tma_smem_raw[];
   TmaSmem *sm = reinterpret_cast<TmaSmem *>(tma_smem_raw);
   T *hs = reinterpret_cast<T *>(tma_smem_raw + 256);       // kTmaMaxCols coefficients
@@ -284,6 +283,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     }
     mbar_fence_init();
   }
+  pdl_wait();
+  if (*poison) return;
+  if (gate_rsq && !dgks_fired(gate_rsq, gate_w1sq)) return;
   for (int c = threadIdx.x; c < ncols; c += blockDim.x) hs[c] = h[c];
   __syncthreads();
 
@@ -338,6 +340,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       }
     }
   }
+  pdl_trigger();
   publish_and_reduce<T, CPW>(acc, nacc, SPEC, true, ncols, warp, lane, partials, cout, nrm2_out, ticket, &sm->is_last, pv);
 }
 

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(256)
     spmv_csr_vector_kernel(int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
                            const T *__restrict__ vals, const T *__restrict__ x, T *__restrict__ y,
                            const int *poison, const __grid_constant__ PeerView pv, int wait_x) {
+  pdl_wait();
   if (*poison) return;
   if (wait_x) {  // multi-GPU: x is pushed by the peers (peer_comm.cuh); wait until every slice has landed
     if (threadIdx.x == 0) peer_x_wait(pv);
