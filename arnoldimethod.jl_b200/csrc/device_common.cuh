@@ -96,26 +96,13 @@ __device__ __forceinline__ double2 ldg_stream(const double2 *p) {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// Device-side record of one Arnoldi / re-seed step.  All decisions of
-// src/expansion.jl:91,99 are taken on the device from these (all-reduced) scalars so
-// that a whole sweep can be enqueued without a host round trip.
-struct StepScalars {
-  double rsq;   // ||v||^2 before orthogonalisation            (expansion.jl:81)
-  double w1sq;  // ||v||^2 after the first Gram-Schmidt pass   (expansion.jl:88)
-  double w2sq;  // ||v||^2 after the DGKS correction pass      (expansion.jl:96)
-  double pad;
-};
-
+// Sweep state shared by the kernels of one workspace.  All decisions of src/expansion.jl:91,99 are taken
+// on the device from (all-reduced) scalars so that a whole sweep can be enqueued without a host round trip.
 struct SweepState {
   int poison;          // != 0: step index (1-based) whose orthogonalisation broke down
   int pad0;
   unsigned long long second_passes;
   unsigned int ticket[8];  // last-block-done counters (one per reduction kernel kind)
 };
-
-__device__ __forceinline__ bool need_second_pass(const StepScalars &s) {
-  // wnorm < eta * rnorm (expansion.jl:91), norms recomputed from the squared sums
-  return sqrt(s.w1sq) < kEta * sqrt(s.rsq);
-}
 
 }  // namespace b2a

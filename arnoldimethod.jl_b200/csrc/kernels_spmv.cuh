@@ -156,11 +156,4 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// ---- one-time CSC -> CSR transpose on the device (mode 0 of b2a_csc_create) ----
-__global__ void count_rows_kernel(int64_t nnz, const int32_t *__restrict__ rowind, unsigned long long *counts) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride)
-    atomicAdd(counts + rowind[i], 1ull);
-}
-
 }  // namespace b2a

@@ -72,9 +72,16 @@ def make_v1(n_global, row_offset, n_local, seed=1):
     return rng.random(n_local)
 
 
-def step_bytes_model(n, nnz, j, passes, s=8):
-    """B_step(j, p) = B_spmv + p * B_cgs(j) + B_scal."""
-    return nnz * (s + 4) + 8 * (n + 1) + 2 * n * s + passes * (2 * j + 3) * n * s + 2 * n * s
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of
+# this workload (profiles/r1_ncu_full_summary.txt); None where no capture exists
+NCU_TRAFFIC_BYTES = {"spmv": 216.4e6}
+LIMITER_NOTES = {
+    "spmv": "uniformly random columns: every 8-byte gather of x moves a 32-byte sector through L2->L1; ncu: "
+            "lts__throughput 70 %, l1tex__throughput 72 % of peak, DRAM traffic == algorithmic bytes. "
+            "HBM-bound only on structured matrices (7-pt stencil: 4.85 TB/s = 74 % of peak).",
+    "cgs_update": "HBM stream of the Krylov panel through a TMA ring (fused update + speculative dots)",
+    "cgs_dots": "HBM stream of the Krylov panel through a TMA ring",
+}
 
 
 # --------------------------------------------------------------------------- clock sampler
@@ -336,7 +343,15 @@ def run_gpu(args):
                     "share_of_kernel_time": round(kern[top]["ms"] / total_ms, 3),
                     "algo_bytes_per_launch": kern[top]["algo_bytes_per_launch"],
                     "avg_launch_us": kern[top]["avg_us"], "kernels": kern}
-        # all-kernel aggregate against the same peak, for context
+        roofline["traffic"] = NCU_TRAFFIC_BYTES.get(top)
+        roofline["limiter"] = LIMITER_NOTES.get(top)
+        # context: the HBM-streaming Gram-Schmidt sweeps (dots + update) taken together, and all kernels
+        gs = [prof[k] for k in ("cgs_dots", "cgs_update") if prof[k]["launches"]]
+        if gs:
+            gs_ms, gs_bytes = sum(r["ms"] for r in gs), sum(r["bytes"] for r in gs)
+            roofline["gram_schmidt"] = {"achieved": round(gs_bytes / (gs_ms * 1e-3) / 1e9, 1), "unit": "GB/s",
+                                        "frac": round(gs_bytes / (gs_ms * 1e-3) / 1e9 / peak, 4),
+                                        "share_of_kernel_time": round(gs_ms / total_ms, 3)}
         roofline["all_kernels_gbs"] = round(sum(r["bytes"] for r in prof.values()) / (total_ms * 1e-3) / 1e9, 1)
 
     # ---------------- e2e arm: host CSR in pinned memory -> upload -> solve -> download Q, R, eigenvalues

@@ -394,3 +394,29 @@ def test_generic_method_on_device_ops(ctx, T):
         assert np.array_equal(ws1.get_cols(1, 1), ws1.get_cols(j + 1, 1))
         ws1.close()
         ws2.close()
+
+
+def test_csr_from_device_arrays(ctx):
+    """b2a_csr_create_device: operator over CSR arrays that already live in HBM (borrowed, not copied)."""
+    import ctypes as C
+
+    import torch
+    from arnoldimethod_jl_b200 import _lib as L
+
+    rng = np.random.default_rng(88)
+    n = 10007
+    A = random_csr(rng, np.float64, n, 6, ragged=True)
+    d_ptr = torch.from_numpy(A.indptr.astype(np.int64)).cuda()
+    d_idx = torch.from_numpy(A.indices.astype(np.int32)).cuda()
+    d_val = torch.from_numpy(A.data).cuda()
+    torch.cuda.synchronize()
+    h = C.c_void_p()
+    L.check(L.lib().b2a_csr_create_device(ctx._h, L.F64, n, n, 0, A.nnz, d_ptr.data_ptr(), d_idx.data_ptr(),
+                                          d_val.data_ptr(), C.byref(h)))
+    op = b2a.Operator(ctx, h, np.float64, n, n, 0, keep=(d_ptr, d_idx, d_val))
+    ws = b2a.ArnoldiWorkspace(n, 2, ctx=ctx)
+    x = rng.standard_normal(n)
+    ws.set_col(1, x)
+    ws.matvec(op, 1, 2)
+    assert np.abs(ws.get_cols(2, 1)[:, 0] - A @ x).max() < 1e-12
+    assert op.bytes_per_matvec == A.nnz * 12 + 8 * (n + 1) + 16 * n
