@@ -354,6 +354,11 @@ def run_gpu(args):
                                         "share_of_kernel_time": round(gs_ms / total_ms, 3)}
         roofline["all_kernels_gbs"] = round(sum(r["bytes"] for r in prof.values()) / (total_ms * 1e-3) / 1e9, 1)
 
+    # the resident workspace / operator are done: release them (at N > 1 this also hands the context's NVLink
+    # peer block to the e2e workspaces)
+    ws.close()
+    op.close()
+
     # ---------------- e2e arm: host CSR in pinned memory -> upload -> solve -> download Q, R, eigenvalues
     def e2e_step():
         op2 = b2a.Operator.from_csr_arrays(ctx, indptr_p, indices_p, data_p, n_global, row_offset=off)
