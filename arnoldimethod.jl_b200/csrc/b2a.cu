@@ -788,6 +788,46 @@ static bool try_rotate(b2a_ws *ws, int col0, int K, int N, int move_src, int mov
   return true;
 }
 
+template <class DT, int NB>
+static bool try_rotate2_inst(b2a_ws *ws, int col0, int K, int N, int move_src, int move_dst, int per, int nchunks) {
+  const size_t smem = ((size_t)(K + 1) * b2a::kRot2Rows + (size_t)4 * nchunks * K * 8) * sizeof(DT);
+  if (smem > 200 * 1024) return false;
+  auto kern = b2a::rotate_basis2_kernel<DT, NB>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  const int64_t grid = std::max<int64_t>(1, cdiv(ws->n_local, b2a::kRot2Rows));
+  prof_begin(ws->ctx, B2A_K_ROTATE, (double)ws->n_local * sizeof(DT) * (K + N + (move_dst >= 0 ? 2.0 : 0.0)));
+  kern<<<(unsigned)grid, 256, smem, ws->ctx->stream>>>(reinterpret_cast<DT *>(ws->dV), ws->ld, col0, K, N,
+                                                         reinterpret_cast<const DT *>(ws->dQ), move_src, move_dst, per,
+                                                         nchunks);
+  prof_end(ws->ctx);
+  ws->ctx->launches++;
+  return true;
+}
+// register-blocked rotation: outputs split over 4 thread groups, NB (<= 8) outputs per chunk
+template <class DT> static bool try_rotate2(b2a_ws *ws, int col0, int K, int N, int move_src, int move_dst) {
+  if (getenv("B2A_ROTATE_V1")) return false;
+  // ComplexF64 is FP64-FMA bound either way (23 TFLOP/s at K = 60, N = 45) and measured slightly faster with
+  // the 1-row x 4-output kernel (1874 vs 2009 us at n = 2e6); Float64 gains from the halved smem traffic
+  // (152 -> 127 us at cfg 2, 1325 -> 1204 us at 256^3)
+  if (b2a::Scalar<DT>::is_complex) return false;
+  const int per = (N + 3) / 4;
+  const int nchunks = (per + 7) / 8;
+  const int nb = (per + nchunks - 1) / nchunks;
+  switch (nb) {
+    case 1: return try_rotate2_inst<DT, 1>(ws, col0, K, N, move_src, move_dst, per, nchunks);
+    case 2: return try_rotate2_inst<DT, 2>(ws, col0, K, N, move_src, move_dst, per, nchunks);
+    case 3: return try_rotate2_inst<DT, 3>(ws, col0, K, N, move_src, move_dst, per, nchunks);
+    case 4: return try_rotate2_inst<DT, 4>(ws, col0, K, N, move_src, move_dst, per, nchunks);
+    case 5: return try_rotate2_inst<DT, 5>(ws, col0, K, N, move_src, move_dst, per, nchunks);
+    case 6: return try_rotate2_inst<DT, 6>(ws, col0, K, N, move_src, move_dst, per, nchunks);
+    case 7: return try_rotate2_inst<DT, 7>(ws, col0, K, N, move_src, move_dst, per, nchunks);
+    default: return try_rotate2_inst<DT, 8>(ws, col0, K, N, move_src, move_dst, per, nchunks);
+  }
+}
+
 // V[:, col0 : col0+N) <- V[:, col0 : col0+K) * Qp  (Qp = K x N packed, host), optional column move
 template <class HT>
 static int rotate(b2a_ws *ws, int col0, int K, int N, const HT *Qp, int move_src, int move_dst) {
@@ -796,7 +836,8 @@ static int rotate(b2a_ws *ws, int col0, int K, int N, const HT *Qp, int move_src
   ws->x_pushed_col = -1;
   if (move_src == move_dst) move_src = move_dst = -1;
   CUDA_TRY(cudaMemcpyAsync(ws->dQ, Qp, (size_t)K * N * sizeof(HT), cudaMemcpyHostToDevice, ws->ctx->stream));
-  bool ok = try_rotate<DT, 128>(ws, col0, K, N, move_src, move_dst);
+  bool ok = try_rotate2<DT>(ws, col0, K, N, move_src, move_dst);
+  if (!ok) ok = try_rotate<DT, 128>(ws, col0, K, N, move_src, move_dst);
   if (!ok) ok = try_rotate<DT, 64>(ws, col0, K, N, move_src, move_dst);
   if (!ok) ok = try_rotate<DT, 32>(ws, col0, K, N, move_src, move_dst);
   if (!ok) return fail(B2A_ERR_ARGUMENT, "basis rotation: Krylov dimension too large for one shared-memory tile");
@@ -1689,7 +1730,6 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
   if (const char *e = getenv("B2A_TMA_STAGES")) ws->tune_stages = atoi(e);
   if (const char *e = getenv("B2A_FINISH_GRID")) ws->finish_grid_mult = std::max(1, atoi(e));
   if (const char *e = getenv("B2A_PEER_X")) ws->peer_x = e[0] != '0';
-  if (const char *e = getenv("B2A_TMA_CTAS")) ws->tune_ctas = std::max(1, std::min(2, atoi(e)));
   if (const char *e = getenv("B2A_TMA_L2PROMO")) ws->tune_l2promo = std::max(0, std::min(3, atoi(e)));
   CUDA_TRY(dev_alloc(ctx, &ws->dV, (size_t)ws->ld * m1 * es));
   CUDA_TRY(cudaMemsetAsync(ws->dV, 0, (size_t)ws->ld * m1 * es, ctx->stream));  // padding rows stay zero forever

@@ -210,7 +210,7 @@ struct TmaSmem {
 // S1: h[c] = sum_r conj(V[r,c]) v[r], nrm2 = ||v||^2
 // ---------------------------------------------------------------------------------------
 template <class T, int CPW>
-__global__ void __launch_bounds__(kTmaThreads, 2)
+__global__ void __launch_bounds__(kTmaThreads, 1)
     cgs_dots_tma_kernel(const __grid_constant__ CUtensorMap tmap, int ncols, TmaGeom g,
                         T *__restrict__ partials, T *__restrict__ hout, double *__restrict__ nrm2_out,
                         unsigned int *ticket, const int *poison, const double *gate_rsq, const double *gate_w1sq,
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kTmaThreads, 2)
 //          stage.  Phase 2 (SPEC): the warp-owns-columns dot of S1 on the updated tile.
 // ---------------------------------------------------------------------------------------
 template <class T, int CPW, bool SPEC>
-__global__ void __launch_bounds__(kTmaThreads, 2)
+__global__ void __launch_bounds__(kTmaThreads, 1)
     cgs_update_tma_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ v, int ncols, TmaGeom g,
                           const T *__restrict__ h, T *__restrict__ partials, T *__restrict__ cout,
                           double *__restrict__ nrm2_out, unsigned int *ticket, const int *poison,

@@ -71,6 +71,82 @@ __global__ void __launch_bounds__(256)
   if (move_dst >= 0 && og == 0 && gr < n) V[(int64_t)move_dst * ld + gr] = tile[K * R + row];
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Register-blocked variant (default): tile of 128 rows, 256 threads = 64 row pairs x 4 output groups.
+// Each thread owns TWO rows and NB outputs (NB = outputs per group, 1..8, template) and keeps the
+// 2 x NB accumulators in registers: per panel column one vector load of the two tile values and
+// NB broadcast loads of Q feed 2*NB FMAs (the 1-row x 4-output kernel above needs 3 shared-memory
+// loads per 4 FMAs and is shared-memory bound).  Outputs are split evenly over the four groups
+// (per = ceil(N/4), in `nchunks` chunks of NB), so no group idles.  Rows past n are the zero padding
+// of the workspace (ld is a multiple of 1024), so neither loads nor stores need masks.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRot2Rows = 128;
+
+template <class T, int NB>
+__global__ void __launch_bounds__(256)
+    rotate_basis2_kernel(T *__restrict__ V, int64_t ld, int col0, int K, int N,
+                         const T *__restrict__ Qd /* K x N, column-major, ld = K */, int move_src, int move_dst,
+                         int per, int nchunks) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int R = kRot2Rows;
+  T *tile = reinterpret_cast<T *>(smem_raw);   // (K+1) x R
+  T *Qs = tile + (size_t)(K + 1) * R;          // [4 groups][nchunks][K][8]
+  const int tid = threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * R;
+
+  const int qtotal = 4 * nchunks * K * 8;
+  for (int idx = tid; idx < qtotal; idx += 256) {
+    const int i = idx & 7;
+    const int c = (idx >> 3) % K;
+    const int ch = ((idx >> 3) / K) % nchunks;
+    const int g = (idx >> 3) / (K * nchunks);
+    const int o = g * per + ch * NB + i;
+    const bool ok = i < NB && o < N && o < (g + 1) * per;
+    Qs[idx] = ok ? Qd[(size_t)o * K + c] : Scalar<T>::zero();
+  }
+  const int ncopy = (move_dst >= 0) ? K + 1 : K;
+  for (int idx = tid; idx < ncopy * R; idx += 256) {
+    const int c = idx / R, row = idx % R;
+    const int src = (c == K) ? move_src : col0 + c;
+    tile[idx] = V[(int64_t)src * ld + r0 + row];
+  }
+  __syncthreads();
+
+  const int rp = tid & 63, g = tid >> 6;
+  const int row = 2 * rp;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    T acc0[NB], acc1[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) acc0[i] = acc1[i] = Scalar<T>::zero();
+    const T *q = Qs + (size_t)(g * nchunks + ch) * K * 8;
+#pragma unroll 2
+    for (int c = 0; c < K; ++c) {
+      const T v0 = tile[c * R + row], v1 = tile[c * R + row + 1];
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        const T qi = q[c * 8 + i];
+        acc0[i] = Scalar<T>::fma_(v0, qi, acc0[i]);
+        acc1[i] = Scalar<T>::fma_(v1, qi, acc1[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int o = g * per + ch * NB + i;
+      if (o < N && o < (g + 1) * per) {
+        T *out = V + (int64_t)(col0 + o) * ld + r0 + row;
+        out[0] = acc0[i];
+        out[1] = acc1[i];
+      }
+    }
+  }
+  if (move_dst >= 0 && g == 0) {
+    T *out = V + (int64_t)move_dst * ld + r0 + row;
+    out[0] = tile[K * R + row];
+    out[1] = tile[K * R + row + 1];
+  }
+}
+
 // X[:, 0:N) = V[:, 0:K) * Y   with Y complex (partialeigen, src/eigvals.jl:94); out of place.
 template <class T>
 __global__ void __launch_bounds__(256)

@@ -70,7 +70,10 @@ def main():
         kw = dict(nev=30, which="LM", tol=1e-6, mindim=30, maxdim=60, restarts=2)
         T = np.complex128
     v1 = rng.random(n).astype(T)
+    P = None
     for rep in range(2):  # warm-up, then measured with per-kernel events
+        if P is not None:
+            P.workspace.close()  # give the pool its memory back before the measured repetition
         ctx.profile(rep == 1)
         ctx.synchronize()
         t0 = time.perf_counter()
