@@ -75,6 +75,34 @@ def main():
         if rank == 0:
             print(f"{T.__name__}: world={world} mvproducts={hist.mvproducts} (oracle {ho.mvproducts}) "
                   f"H err={err:.1e} ||AQ-QR||={res:.2e}", flush=True)
+    # breakdown under sharding (test/expansion.jl:34-55 shape): block-diagonal A, v1 = e1 -> the Krylov space is
+    # invariant after 4 steps: H[5,4] == 0 exactly on every rank, the re-seeded column (global-row keyed RNG,
+    # identical for every GPU count) keeps V orthonormal, and the sweep resumes
+    rng = np.random.default_rng(9)
+    nb = 4
+    n = 4096
+    B = np.zeros((n, n))
+    B[:nb, :nb] = rng.random((nb, nb))
+    B[nb:, nb:] = np.diag(np.linspace(1, 2, n - nb)) + 0.01 * rng.random((n - nb, n - nb))
+    e1 = np.zeros(n)
+    e1[0] = 1
+    ws = b2a.ArnoldiWorkspace(e1, 8, ctx=ctx)
+    op = b2a.Operator.from_matrix(ctx, sp.csr_matrix(B))
+    st = ws.iterate_arnoldi(op, 1, 8, seed=3)
+    H = np.array(ws.H)
+    assert H[4, 3] == 0 and st.breakdowns == 1, (H[4, 3], st.breakdowns)
+    Vl = ws.get_cols(1, 9)
+    parts = [torch.zeros((int(c), 9), dtype=torch.float64, device="cuda") for c in b2a.sharding.row_partition(n, world)[1]]
+    dist.all_gather(parts, torch.from_numpy(np.ascontiguousarray(Vl)).cuda())
+    V = torch.cat(parts).cpu().numpy()
+    assert np.linalg.norm(V.T @ V - np.eye(9)) < 1e-13
+    assert np.linalg.norm(B @ V[:, :8] - V @ H) < 1e-12
+    # the re-seeded vector does not depend on the number of GPUs
+    if rank == 0:
+        np.save("/tmp/b2a_reseed_check.npy", V[:, 4])
+        print(f"breakdown: world={world} H[5,4]={H[4, 3]} breakdowns={st.breakdowns} ||V'V-I||={np.linalg.norm(V.T @ V - np.eye(9)):.1e}", flush=True)
+    ws.close()
+
     dist.barrier()
     if rank == 0:
         print("DIST_GPU_CHECK_OK", flush=True)
