@@ -273,6 +273,7 @@ struct b2a_ws {
   b2a::PeerView peer;            // P == 1 when disabled; the block itself is owned by the context
   bool peer_borrowed = false;
   int finish_grid_mult = 4;
+  bool push_separate = false;  // experiment: push x with its own kernel instead of inside cgs_finish
   bool peer_x = true;  // fused x push (B2A_PEER_X=0: NCCL all-gather for x, in-kernel all-reduce kept)
   int x_pushed_col = -1;  // 0-based column whose normalised content currently sits in every rank's x buffer
   int tune_rt_dots = 0, tune_rt_upd = 0, tune_stages = 0, tune_ctas = 1, tune_l2promo = 2;  // experiment overrides (env)
@@ -611,7 +612,7 @@ template <class DT> static int enqueue_cgs(b2a_ws *ws, int j, int mode, int step
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * ws->finish_grid_mult, cdiv(nvec, 256 * 4)));
   DT *Hcol = reinterpret_cast<DT *>(ws->dH) + (int64_t)(std::max(j, 1) - 1) * (ws->maxdim + 1);
   prof_begin(ctx, B2A_K_FINISH, 2.0 * ws->n_local * sizeof(DT));
-  const int push = (mode == 0 && ws->peer.P > 1 && ws->peer_x) ? 1 : 0;  // Arnoldi step: the new column is the next mat-vec input
+  const int push = (mode == 0 && ws->peer.P > 1 && ws->peer_x && !ws->push_separate) ? 1 : 0;  // Arnoldi step: the new column is the next mat-vec input
   CUDA_TRY(launch_pdl(b2a::cgs_finish_kernel<DT>, (unsigned)grid, 256u, 0, ctx->stream, v, ws->n_local, j,
                       (const DT *)h1, (const DT *)h2, (const double *)rsq, (const double *)w1sq,
                       (const double *)ws->w2sq, Hcol, ws->dinfo + j, ws->state, step, mode, ws->peer, ws->row_offset,
@@ -709,7 +710,9 @@ template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, 
     // has already pushed this column into every rank's x buffer; otherwise push it explicitly
     if (ws->x_pushed_col != jsrc0) {
       const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 4, cdiv(ws->n_local, 256)));
+      prof_begin(ctx, B2A_K_FILL, (double)ws->n_local * sizeof(DT) * ws->peer.P);
       b2a::xpush_kernel<DT><<<(unsigned)grid, 256, 0, ctx->stream>>>(xl, ws->n_local, ws->state, ws->peer, ws->row_offset);
+      prof_end(ctx);
       ctx->launches++;
       CUDA_TRY(cudaGetLastError());
       ws->x_pushed_col = jsrc0;
@@ -1730,6 +1733,7 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
   if (const char *e = getenv("B2A_TMA_STAGES")) ws->tune_stages = atoi(e);
   if (const char *e = getenv("B2A_FINISH_GRID")) ws->finish_grid_mult = std::max(1, atoi(e));
   if (const char *e = getenv("B2A_PEER_X")) ws->peer_x = e[0] != '0';
+  if (const char *e = getenv("B2A_PUSH_SEPARATE")) ws->push_separate = e[0] == '1';
   if (const char *e = getenv("B2A_TMA_L2PROMO")) ws->tune_l2promo = std::max(0, std::min(3, atoi(e)));
   CUDA_TRY(dev_alloc(ctx, &ws->dV, (size_t)ws->ld * m1 * es));
   CUDA_TRY(cudaMemsetAsync(ws->dV, 0, (size_t)ws->ld * m1 * es, ctx->stream));  // padding rows stay zero forever
