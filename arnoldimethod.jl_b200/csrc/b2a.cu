@@ -238,6 +238,9 @@ struct b2a_op {
   int32_t *d_tile_row = nullptr;
   int ntiles = 0, tma_stages = 0;
   bool use_tma = false;
+  // column blocking (x larger than L2 and scattered columns): block-major CSR, d_ptr holds nblocks row-pointer
+  // arrays of n_local+1 entries each (absolute positions in d_idx / d_vals)
+  int nblocks = 1;
   b2a_matvec_fn fn = nullptr;
   void *user = nullptr;
 };
@@ -636,13 +639,31 @@ static void launch_spmv_vec_u(b2a_op *A, const DT *x, DT *y, const int *poison, 
                               const XWait &xw) {
   const int64_t threads = cdiv(A->n_local, U) * LPR;
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * A->grid_mult, cdiv(threads, 256)));
-  (void)launch_pdl(b2a::spmv_csr_vector_kernel<DT, LPR, U>, (unsigned)grid, 256u, 0, st, A->n_local,
+  (void)launch_pdl(b2a::spmv_csr_vector_kernel<DT, LPR, U, false>, (unsigned)grid, 256u, 0, st, A->n_local,
                    (const int64_t *)A->d_ptr, (const int32_t *)A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y,
-                   poison, xw.pv, xw.wait);
+                   poison, xw.pv, xw.wait, 0);
+}
+// column-blocked operator: one pass per block, L2-hinted loads, the first pass writes y, the others accumulate
+template <class DT, int LPR>
+static void launch_spmv_blocked(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms,
+                                const XWait &xw, int64_t *launches) {
+  constexpr int U = 2;
+  const int64_t threads = cdiv(A->n_local, U) * LPR;
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * A->grid_mult, cdiv(threads, 256)));
+  for (int b = 0; b < A->nblocks; ++b) {
+    (void)launch_pdl(b2a::spmv_csr_vector_kernel<DT, LPR, U, true>, (unsigned)grid, 256u, 0, st, A->n_local,
+                     (const int64_t *)(A->d_ptr + (size_t)b * (A->n_local + 1)), (const int32_t *)A->d_idx,
+                     reinterpret_cast<const DT *>(A->d_vals), x, y, poison, xw.pv, b == 0 ? xw.wait : 0, b > 0 ? 1 : 0);
+    if (b > 0) ++*launches;
+  }
 }
 template <class DT, int LPR>
 static void launch_spmv_vec(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms,
                             const XWait &xw) {
+  if (A->nblocks > 1) {
+    launch_spmv_blocked<DT, LPR>(A, x, y, poison, st, sms, xw, &A->ctx->launches);
+    return;
+  }
   switch (A->rows_in_flight) {
     case 1: launch_spmv_vec_u<DT, LPR, 1>(A, x, y, poison, st, sms, xw); break;
     case 4: launch_spmv_vec_u<DT, LPR, 4>(A, x, y, poison, st, sms, xw); break;
@@ -748,12 +769,16 @@ template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, 
       case 16: launch_spmv_csc<DT, 16>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
       default: launch_spmv_csc<DT, 32>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
     }
-  } else if (A->use_tma && ctx->world == 1) {
+  } else if (A->use_tma && ctx->world == 1 && A->nblocks == 1) {
     B2A_TRY(launch_spmv_tma<DT>(A, x, y, poison, ctx));
   } else {
     switch (A->lpr) {
       case 1: {
         const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, cdiv(A->n_local, 256)));
+        if (A->nblocks > 1) {
+          launch_spmv_blocked<DT, 2>(A, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches);
+          break;
+        }
         b2a::spmv_csr_scalar_kernel<DT><<<(unsigned)grid, 256, 0, ctx->stream>>>(
             A->n_local, A->d_ptr, A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y, poison, xw.pv, xw.wait);
         break;
@@ -1347,6 +1372,67 @@ static int check_op_args(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_glo
   return B2A_OK;
 }
 
+// ---- column blocking -------------------------------------------------------------------------
+// Decide the number of column blocks: only when x does not fit a comfortable share of L2 AND the columns are
+// scattered (mean |col - row| far beyond an L2-sized window); banded / stencil operators are left alone.
+// B2A_SPMV_BLOCK_MB: unset/-1 = automatic, 0 = never, > 0 = force blocks of that many MB of x.
+extern "C++" {
+template <class RP, class CI>
+static int decide_col_blocks(RP rp, CI ci, int64_t n_rows, int64_t n_global, int64_t row_offset, size_t es) {
+  double block_mb = -1.0;
+  if (const char *e = getenv("B2A_SPMV_BLOCK_MB")) block_mb = atof(e);
+  if (block_mb == 0.0 || n_rows == 0) return 1;
+  const double x_bytes = (double)n_global * (double)es;
+  if (block_mb > 0.0) return (int)std::min<double>(4096.0, std::max(1.0, std::ceil(x_bytes / (block_mb * 1048576.0))));
+  if (x_bytes <= 48.0 * 1048576.0) return 1;
+  // scatter estimate on a sample of rows
+  const int64_t step = std::max<int64_t>(1, n_rows / 4096);
+  double sum = 0.0;
+  int64_t cnt = 0;
+  for (int64_t r = 0; r < n_rows; r += step)
+    for (int64_t i = rp(r); i < rp(r + 1); ++i) {
+      sum += std::fabs((double)(ci(i) - (row_offset + r)));
+      ++cnt;
+    }
+  if (cnt == 0 || sum / (double)cnt * (double)es < 8.0 * 1048576.0) return 1;
+  return (int)std::min<double>(4096.0, std::ceil(x_bytes / (32.0 * 1048576.0)));
+}
+
+// Reorder the CSR entries block-major (stable counting sort by (column block, row)): bptr gets nblocks row-pointer
+// arrays, bcol / bval the permuted entries.
+template <class RP, class CI>
+static void build_col_blocks(RP rp, CI ci, const char *vals, size_t es, int64_t n_rows, int64_t n_global, int nblocks,
+                             std::vector<int64_t> &bptr, std::vector<int32_t> &bcol, std::vector<char> &bval) {
+  const int64_t W = cdiv(n_global, nblocks);
+  const int64_t nnz = rp(n_rows);
+  const size_t stride = (size_t)n_rows + 1;
+  bptr.assign(stride * nblocks, 0);
+  for (int64_t r = 0; r < n_rows; ++r)
+    for (int64_t i = rp(r); i < rp(r + 1); ++i) bptr[(size_t)(ci(i) / W) * stride + r + 1]++;
+  int64_t run = 0;
+  for (int b = 0; b < nblocks; ++b) {
+    int64_t *p = bptr.data() + (size_t)b * stride;
+    p[0] = run;
+    for (int64_t r = 0; r < n_rows; ++r) {
+      run += p[r + 1];
+      p[r + 1] = run;
+    }
+  }
+  bcol.resize((size_t)std::max<int64_t>(nnz, 1));
+  bval.resize((size_t)std::max<int64_t>(nnz, 1) * es);
+  std::vector<int64_t> cur((size_t)nblocks);
+  for (int64_t r = 0; r < n_rows; ++r) {
+    for (int b = 0; b < nblocks; ++b) cur[b] = bptr[(size_t)b * stride + r];
+    for (int64_t i = rp(r); i < rp(r + 1); ++i) {
+      const int64_t c = ci(i);
+      const int64_t dst = cur[(size_t)(c / W)]++;
+      bcol[(size_t)dst] = (int32_t)c;
+      std::memcpy(&bval[(size_t)dst * es], vals + (size_t)i * es, es);
+    }
+  }
+}
+}  // extern "C++"
+
 int b2a_csr_create(b2a_ctx *ctx, int dtype, int64_t n_rows_local, int64_t n_global, int64_t row_offset, int64_t nnz,
                    const void *rowptr, const void *colind, const void *vals, int idx_width, int idx_base,
                    b2a_op **out) {
@@ -1362,6 +1448,42 @@ int b2a_csr_create(b2a_ctx *ctx, int dtype, int64_t n_rows_local, int64_t n_glob
   op->nnz = nnz;
   op->lpr = pick_lanes(nnz, n_rows_local);
   op_tuning(op);
+  // column blocking decision (host pass over a sample of rows) and, if taken, the block-major reordering
+  {
+    auto rp32 = [&](int64_t r) { return (int64_t) reinterpret_cast<const int32_t *>(rowptr)[r] - idx_base; };
+    auto rp64 = [&](int64_t r) { return reinterpret_cast<const int64_t *>(rowptr)[r] - idx_base; };
+    auto ci32 = [&](int64_t i) { return (int64_t) reinterpret_cast<const int32_t *>(colind)[i] - idx_base; };
+    auto ci64 = [&](int64_t i) { return reinterpret_cast<const int64_t *>(colind)[i] - idx_base; };
+    const size_t es = dtype_size(dtype);
+    op->nblocks = idx_width == 32 ? decide_col_blocks(rp32, ci32, n_rows_local, n_global, row_offset, es)
+                                  : decide_col_blocks(rp64, ci64, n_rows_local, n_global, row_offset, es);
+    if (op->nblocks > 1) {
+      std::vector<int64_t> bptr;
+      std::vector<int32_t> bcol;
+      std::vector<char> bval;
+      if (idx_width == 32)
+        build_col_blocks(rp32, ci32, reinterpret_cast<const char *>(vals), es, n_rows_local, n_global, op->nblocks, bptr, bcol, bval);
+      else
+        build_col_blocks(rp64, ci64, reinterpret_cast<const char *>(vals), es, n_rows_local, n_global, op->nblocks, bptr, bcol, bval);
+      op->lpr = pick_lanes(nnz, n_rows_local * op->nblocks);
+      if (const char *e = getenv("B2A_SPMV_LPR")) op->lpr = atoi(e);
+      int sb = op_alloc(ctx, op, (int64_t)bptr.size() - 1);
+      if (sb == B2A_OK) sb = upload_index(ctx, bptr.data(), (int64_t)bptr.size(), 64, 0, op->d_ptr, nullptr);
+      if (sb == B2A_OK) sb = upload_index(ctx, bcol.data(), nnz, 32, 0, nullptr, op->d_idx);
+      if (sb == B2A_OK && nnz > 0) {
+        cudaError_t e = cudaMemcpyAsync(op->d_vals, bval.data(), (size_t)nnz * es, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) sb = fail(B2A_ERR_CUDA, cudaGetErrorString(e));
+      }
+      if (sb == B2A_OK) sb = cudaStreamSynchronize(ctx->stream) == cudaSuccess ? B2A_OK : fail(B2A_ERR_CUDA, "sync");
+      if (sb != B2A_OK) {
+        b2a_op_destroy(op);
+        return sb;
+      }
+      *out = op;
+      return B2A_OK;
+    }
+  }
   int s = op_alloc(ctx, op, n_rows_local);
   if (s == B2A_OK) s = upload_index(ctx, rowptr, n_rows_local + 1, idx_width, idx_base, op->d_ptr, nullptr);
   if (s == B2A_OK) s = upload_index(ctx, colind, nnz, idx_width, idx_base, nullptr, op->d_idx);

@@ -420,3 +420,49 @@ def test_csr_from_device_arrays(ctx):
     ws.matvec(op, 1, 2)
     assert np.abs(ws.get_cols(2, 1)[:, 0] - A @ x).max() < 1e-12
     assert op.bytes_per_matvec == A.nnz * 12 + 8 * (n + 1) + 16 * n
+
+
+@pytest.mark.parametrize("T", TYPES)
+@pytest.mark.parametrize("block_mb", ["0.02", "0.05", "0.3"])
+def test_spmv_column_blocked(ctx, monkeypatch, T, block_mb):
+    """Column-blocked (block-major CSR, one pass per block, accumulate) SpMV equals SciPy; forced through
+    B2A_SPMV_BLOCK_MB on a small matrix (automatic mode only triggers when x exceeds 48 MB)."""
+    monkeypatch.setenv("B2A_SPMV_BLOCK_MB", block_mb)
+    rng = np.random.default_rng(91)
+    n = 20011
+    for k, ragged in [(15, False), (6, True), (1, False)]:
+        A = random_csr(rng, T, n, k, ragged)
+        op = b2a.Operator.from_matrix(ctx, A)
+        ws = b2a.ArnoldiWorkspace(n, 2, dtype=T, ctx=ctx)
+        x = randn(rng, T, n)
+        ws.set_col(1, x)
+        ws.matvec(op, 1, 2)
+        y = ws.get_cols(2, 1)[:, 0]
+        assert np.abs(y - A @ x).max() <= 64 * EPS * (abs(A) @ abs(x)).max()
+        ws.matvec(op, 1, 2)  # idempotent: the first block pass overwrites y
+        assert np.array_equal(ws.get_cols(2, 1)[:, 0], y)
+    # Julia-style 1-based Int64 input goes through the same builder
+    A = random_csr(rng, T, n, 9, True)
+    op = b2a.Operator.from_csr_arrays(ctx, A.indptr.astype(np.int64) + 1, A.indices.astype(np.int64) + 1, A.data, n, idx_base=1)
+    ws = b2a.ArnoldiWorkspace(n, 2, dtype=T, ctx=ctx)
+    x = randn(rng, T, n)
+    ws.set_col(1, x)
+    ws.matvec(op, 1, 2)
+    assert np.abs(ws.get_cols(2, 1)[:, 0] - A @ x).max() <= 64 * EPS * (abs(A) @ abs(x)).max()
+
+
+def test_partialschur_with_column_blocked_operator(ctx, monkeypatch):
+    monkeypatch.setenv("B2A_SPMV_BLOCK_MB", "0.1")
+    rng = np.random.default_rng(92)
+    n = 40000
+    A = sp.random(n, n, 12 / n, random_state=rng, format="csr") * 0.3
+    d = np.zeros(n)
+    d[:12] = 5 + 20 * 0.8 ** np.arange(12)
+    A = (A + sp.diags(d)).tocsr()
+    v1 = rng.random(n)
+    P, hist = b2a.partialschur(A, nev=6, tol=1e-8, v1=v1)
+    monkeypatch.setenv("B2A_SPMV_BLOCK_MB", "0")
+    P0, hist0 = b2a.partialschur(A, nev=6, tol=1e-8, v1=v1)
+    assert hist.converged and hist.mvproducts == hist0.mvproducts
+    assert np.allclose(np.sort_complex(P.eigenvalues), np.sort_complex(P0.eigenvalues), atol=1e-10)
+    assert np.linalg.norm(A @ P.Q - P.Q @ P.R) < n * 1e-8

@@ -2,6 +2,8 @@
 
     python tools/cfg_bench.py cfg3 [N]     7-point Laplacian N^3 (default 256), nev 10, maxdim 20, :SR, 3 restarts
     python tools/cfg_bench.py cfg4 [n]     ComplexF64 random CSR, 20 nnz/row (default n = 2e6), nev 30, maxdim 60, :LM
+    python tools/cfg_bench.py cfg5shard    one GPU's share of cfg 5 run as a stand-alone problem: Float64 random CSR,
+                                           n = 1.25e7, 15 nnz/row, nev 20, maxdim 40, :LM, 2 restarts
 """
 import json
 import os
@@ -56,6 +58,18 @@ def main():
         indptr, indices, data, n = laplacian_csr(N)
         op = b2a.Operator.from_csr_arrays(ctx, indptr, indices, data, n)
         kw = dict(nev=10, which="SR", tol=1e-6, mindim=10, maxdim=20, restarts=3)
+        T = np.float64
+    elif which == "cfg5shard":
+        n, k = 12_500_000, 15
+        indptr = np.arange(0, (n + 1) * k, k, dtype=np.int64)
+        indices = rng.integers(0, n, size=n * k, dtype=np.int32)
+        indices = np.sort(indices.reshape(n, k), axis=1).ravel()
+        data = rng.standard_normal(n * k) * 0.5
+        d = np.arange(40)
+        data.reshape(n, k)[:40, 0] = 5 + 20 * 0.9 ** d
+        indices.reshape(n, k)[:40, 0] = d
+        op = b2a.Operator.from_csr_arrays(ctx, indptr, indices, data, n)
+        kw = dict(nev=20, which="LM", tol=1e-6, mindim=20, maxdim=40, restarts=2)
         T = np.float64
     else:
         n = int(float(sys.argv[2])) if len(sys.argv) > 2 else 2_000_000

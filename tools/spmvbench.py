@@ -28,19 +28,21 @@ def main():
         n = int(float(args[0])) if args else 1_000_000
         k = int(args[1]) if len(args) > 1 else 16
         indptr = np.arange(0, (n + 1) * k, k, dtype=np.int64)
-        cols = np.sort(rng.integers(0, n, size=(n, k)), axis=1).astype(np.int32).ravel()
+        cols = np.sort(rng.integers(0, n, size=(n, k), dtype=np.int32), axis=1).ravel()
         vals = rng.standard_normal(n * k).astype(T)
         A = sp.csr_matrix((vals, cols, indptr), shape=(n, n))
     x = rng.standard_normal(n).astype(T)
     ref = A @ x
     ctx = b2a.default_context()
     configs = [dict()]
+    if "--blocksweep" in sys.argv:
+        configs = [dict(B2A_SPMV_BLOCK_MB=str(mb)) for mb in (0, 16, 24, 32, 48, -1)]
     if "--sweep" in sys.argv:
         lprs = [int(v) for v in os.environ.get("SWEEP_LPR", "8,16").split(",")]
         configs = [dict(B2A_SPMV_U=str(u), B2A_SPMV_GRID=str(g), B2A_SPMV_LPR=str(l))
                    for l in lprs for u in (2, 4, 8) for g in (8, 16)]
     for cfg in configs:
-        for k_ in ("B2A_SPMV_U", "B2A_SPMV_GRID", "B2A_SPMV_LPR"):
+        for k_ in ("B2A_SPMV_U", "B2A_SPMV_GRID", "B2A_SPMV_LPR", "B2A_SPMV_BLOCK_MB"):
             os.environ.pop(k_, None)
         os.environ.update(cfg)
         op = b2a.Operator.from_matrix(ctx, A)
