@@ -32,6 +32,7 @@
 #include "host_dense.hpp"
 #include "kernels_cgs.cuh"
 #include "kernels_cgs_tma.cuh"
+#include "kernels_cgs_sweep.cuh"
 #include "kernels_rotate.cuh"
 #include "kernels_spmv.cuh"
 #include "kernels_spmv_tma.cuh"
@@ -129,6 +130,8 @@ struct b2a_ctx {
     double bytes;
     int gate_step;  // > 0: launch belongs to the gated second pass of that step
     cudaEvent_t e0, e1;
+    double extra_bytes = 0.0;  // fused sweep: bytes of its gated phase, counted if step `extra_step` ran it
+    int extra_step = 0;
   };
   bool prof_on = false;
   std::vector<ProfRec> prof_pending;
@@ -187,7 +190,7 @@ static cudaEvent_t prof_event(b2a_ctx *c) {
 }
 static inline void prof_begin(b2a_ctx *c, int kind, double bytes, int gate_step = 0) {
   if (!c->prof_on) return;
-  b2a_ctx::ProfRec r{kind, bytes, gate_step, prof_event(c), prof_event(c)};
+  b2a_ctx::ProfRec r{kind, bytes, gate_step, prof_event(c), prof_event(c), 0.0, 0};
   cudaEventRecord(r.e0, c->stream);
   c->prof_pending.push_back(r);
 }
@@ -211,6 +214,10 @@ static void prof_collect(b2a_ctx *c, const int *info, int info_base, int info_co
         c->prof_n[r.kind] += 1;
         c->prof_ms[r.kind] += ms;
         c->prof_bytes[r.kind] += r.bytes;
+        if (r.extra_step > 0) {
+          const int i = r.extra_step - info_base;
+          if (info && i >= 0 && i < info_count && (info[i] & 1)) c->prof_bytes[r.kind] += r.extra_bytes;
+        }
       } else {
         (void)cudaGetLastError();
       }
@@ -278,6 +285,11 @@ struct b2a_ws {
   int finish_grid_mult = 4;
   bool push_separate = false;  // experiment: push x with its own kernel instead of inside cgs_finish
   bool peer_x = true;  // fused x push (B2A_PEER_X=0: NCCL all-gather for x, in-kernel all-reduce kept)
+  // fused orthogonalisation (kernels_cgs_sweep.cuh): 0 = four kernels per step, 1 = one persistent kernel on
+  // single-GPU workspaces, 2 = also on row-sharded ones (B2A_FUSED_SWEEP)
+  int fused_sweep = 0;
+  unsigned long long *sweep_flag = nullptr;  // release flag of the in-kernel grid barriers (monotone epoch)
+  unsigned long long sweep_epoch = 0;
   int x_pushed_col = -1;  // 0-based column whose normalised content currently sits in every rank's x buffer
   int tune_rt_dots = 0, tune_rt_upd = 0, tune_stages = 0, tune_ctas = 1, tune_l2promo = 2;  // experiment overrides (env)
 };
@@ -556,6 +568,61 @@ static int launch_update_tma(b2a_ws *ws, int ncols, DT *v, const DT *h, DT *cout
   }
 }
 
+// ---- fused orthogonalisation: S1 -> S2 -> [S3] -> finish in ONE persistent kernel (kernels_cgs_sweep.cuh) ----
+template <class DT, int CPW>
+static int launch_sweep_inst(b2a_ws *ws, int j, int step, const b2a::TmaGeom &g, size_t smem, int grid, int push) {
+  auto kern = b2a::cgs_sweep_tma_kernel<DT, CPW>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    B2A_TRY(set_smem_attr(kern, smem));
+    attr_done = true;
+  }
+  CUtensorMap tm;
+  if (!make_panel_tmap(ws, j, g.RT, &tm)) return fail(B2A_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  b2a_ctx *ctx = ws->ctx;
+  DT *v = col<DT>(ws, j);
+  DT *h1 = reinterpret_cast<DT *>(ws->hb1);
+  DT *h2 = reinterpret_cast<DT *>(ws->hb2);
+  double *rsq = reinterpret_cast<double *>(h1 + j);
+  double *w1sq = reinterpret_cast<double *>(h2 + j);
+  DT *Hcol = reinterpret_cast<DT *>(ws->dH) + (int64_t)(j - 1) * (ws->maxdim + 1);
+  const double ns = (double)ws->n_local * sizeof(DT);
+  // P1 (j+1) n s + P2 (j+2) n s + P4 2 n s; the gated P3 adds (j+2) n s when it runs
+  prof_begin(ctx, B2A_K_SWEEP, (2.0 * j + 5.0) * ns);
+  if (ctx->prof_on) {
+    ctx->prof_pending.back().extra_bytes = (j + 2.0) * ns;
+    ctx->prof_pending.back().extra_step = j;
+  }
+  const unsigned long long epoch = ws->sweep_epoch;
+  ws->sweep_epoch += 4;
+  CUDA_TRY(launch_pdl(kern, (unsigned)grid, (unsigned)b2a::kTmaThreads, smem, ctx->stream, tm, v, ws->n_local, j, g,
+                      reinterpret_cast<DT *>(ws->partials), h1, h2, rsq, w1sq, ws->w2sq, Hcol, ws->dinfo + j, ws->state,
+                      ws->sweep_flag, epoch, step, ws->peer, ws->row_offset, push));
+  prof_end(ctx);
+  ctx->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return B2A_OK;
+}
+
+// returns 1 when the geometry does not fit (caller falls back to the four-kernel path)
+template <class DT> static int launch_sweep(b2a_ws *ws, int j, int step, int push) {
+  b2a::TmaGeom g;
+  size_t smem;
+  int grid;
+  if (!tma_geometry(ws, j, sizeof(DT), true, false, &g, &smem, &grid)) return 1;
+  if (grid > ws->ctx->num_sms) return 1;  // the in-kernel grid barrier needs every CTA resident
+  switch (std::max(1, (j + 7) / 8)) {
+    case 1: return launch_sweep_inst<DT, 1>(ws, j, step, g, smem, grid, push);
+    case 2: return launch_sweep_inst<DT, 2>(ws, j, step, g, smem, grid, push);
+    case 3: return launch_sweep_inst<DT, 3>(ws, j, step, g, smem, grid, push);
+    case 4: return launch_sweep_inst<DT, 4>(ws, j, step, g, smem, grid, push);
+    case 5: return launch_sweep_inst<DT, 5>(ws, j, step, g, smem, grid, push);
+    case 6: return launch_sweep_inst<DT, 6>(ws, j, step, g, smem, grid, push);
+    case 7: return launch_sweep_inst<DT, 7>(ws, j, step, g, smem, grid, push);
+    default: return launch_sweep_inst<DT, 8>(ws, j, step, g, smem, grid, push);
+  }
+}
+
 static bool tma_path_ok(const b2a_ws *ws, int j, size_t elem) {
   b2a::TmaGeom g;
   size_t smem;
@@ -580,6 +647,17 @@ template <class DT> static int enqueue_cgs(b2a_ws *ws, int j, int mode, int step
   // multi-GPU: the TMA kernels finish their own all-reduce over NVLink peer memory (peer_comm.cuh);
   // otherwise a host-launched NCCL all-reduce follows each reduction kernel
   const bool fused = tma && ws->peer.P > 1;
+  if (mode == 0 && j >= 1 && tma && ws->tune_ctas == 1 &&
+      (ws->fused_sweep >= 2 || (ws->fused_sweep == 1 && ws->peer.P == 1 && ctx->world == 1))) {
+    // the whole orthogonalisation as one persistent kernel with in-kernel grid barriers
+    const int push = (ws->peer.P > 1 && ws->peer_x && !ws->push_separate) ? 1 : 0;
+    const int s = launch_sweep<DT>(ws, j, step, push);
+    if (s == B2A_OK) {
+      ws->x_pushed_col = push ? j : -1;
+      return B2A_OK;
+    }
+    if (s != 1) return s;
+  }
   if (j == 0 || mode == 2) {
     if (tma)
       B2A_TRY(launch_dots_tma<DT>(ws, 0, v, h1, rsq, nullptr, nullptr, 0, false));
@@ -958,6 +1036,7 @@ static int iterate_arnoldi(b2a_ws *ws, b2a_op *A, int from, int to, uint64_t see
     std::memcpy(&state, p + hbytes + ncols * sizeof(int), sizeof(state));
     const int *info = reinterpret_cast<const int *>(p + hbytes);
     prof_collect(ctx, info, j, ncols);
+    if (state.error) return fail(B2A_ERR_CUDA, "fused orthogonalisation: grid barrier timed out");
     const int last = state.poison ? state.poison : to;  // last step that really executed
     const HT *Hn = reinterpret_cast<const HT *>(p);
     for (int s = j; s <= last; ++s) {
@@ -1856,6 +1935,7 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
   if (const char *e = getenv("B2A_FINISH_GRID")) ws->finish_grid_mult = std::max(1, atoi(e));
   if (const char *e = getenv("B2A_PEER_X")) ws->peer_x = e[0] != '0';
   if (const char *e = getenv("B2A_PUSH_SEPARATE")) ws->push_separate = e[0] == '1';
+  if (const char *e = getenv("B2A_FUSED_SWEEP")) ws->fused_sweep = std::max(0, std::min(2, atoi(e)));
   if (const char *e = getenv("B2A_TMA_L2PROMO")) ws->tune_l2promo = std::max(0, std::min(3, atoi(e)));
   CUDA_TRY(dev_alloc(ctx, &ws->dV, (size_t)ws->ld * m1 * es));
   CUDA_TRY(cudaMemsetAsync(ws->dV, 0, (size_t)ws->ld * m1 * es, ctx->stream));  // padding rows stay zero forever
@@ -1879,6 +1959,7 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
   const size_t o_part2 = carve(sizeof(double) * ws->upd_grid_max);
   const size_t o_state = carve(sizeof(b2a::SweepState));
   const size_t o_dQ = carve((size_t)std::max(maxdim * maxdim, 1) * es);
+  const size_t o_flag = carve(sizeof(unsigned long long));
   CUDA_TRY(dev_alloc(ctx, &ws->arena, off));
   CUDA_TRY(cudaMemsetAsync(ws->arena, 0, off, ctx->stream));
   char *base = reinterpret_cast<char *>(ws->arena);
@@ -1891,6 +1972,7 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
   ws->partials2 = reinterpret_cast<double *>(base + o_part2);
   ws->state = reinterpret_cast<b2a::SweepState *>(base + o_state);
   ws->dQ = base + o_dQ;
+  ws->sweep_flag = reinterpret_cast<unsigned long long *>(base + o_flag);
   const size_t want = (size_t)m1 * maxdim * es + sizeof(int) * (m1 + 1) + sizeof(b2a::SweepState) + 64;
   CUDA_TRY(pinned_get(ctx, want, &ws->pinned, &ws->pinned_bytes));
   B2A_TRY(peer_setup(ctx, ws));

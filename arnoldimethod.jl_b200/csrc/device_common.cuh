@@ -100,7 +100,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // on the device from (all-reduced) scalars so that a whole sweep can be enqueued without a host round trip.
 struct SweepState {
   int poison;          // != 0: step index (1-based) whose orthogonalisation broke down
-  int pad0;
+  int error;           // != 0: a grid barrier of the fused sweep kernel timed out (kernels_cgs_sweep.cuh)
   unsigned long long second_passes;
   unsigned int ticket[8];  // last-block-done counters (one per reduction kernel kind)
 };

@@ -1,0 +1,332 @@
+// kernels_cgs_sweep.cuh - one whole orthogonalisation (src/expansion.jl:69-109) as ONE persistent kernel.
+//
+// The four kernels of kernels_cgs_tma.cuh / kernels_cgs.cuh (S1 dots, S2 update + speculative dots,
+// gated S3 update, finish) cost a kernel boundary each: drain, last-CTA reduction, launch, pipeline
+// refill - about 8-10 us per boundary on B200, i.e. ~17 % of an Arnoldi step at n = 1e6.  This kernel
+// runs the same four phases back to back inside one persistent grid (one CTA per SM):
+//
+//   P1  h = V' v, ||v||^2            tiles forward      -> grid barrier A (last CTA reduces, all-reduce)
+//   P2  v -= V h, ||v||^2, c = V' v  tiles BACKWARD     -> grid barrier B
+//   P3  v -= V c, ||v||^2            tiles forward, only if the DGKS test fired (expansion.jl:91)
+//                                                        -> grid barrier C
+//   P4  H[:, j], breakdown test, v ./= wnorm (expansion.jl:95-107), x push to the peers
+//
+// and keeps the shared-memory ring ALIVE across the phases: local tile l always lives in ring slot
+// l % stages, so when the walking direction flips, the `stages` tiles the previous phase touched last
+// are still on chip and are re-used without a reload (no pipeline bubble after a barrier, and
+// stages x tile bytes per SM less HBM traffic per phase change).  A grid barrier is a ticket + a
+// release flag (st.release.gpu / ld.acquire.gpu on a monotone epoch); all CTAs are co-resident by
+// construction (grid <= #SMs, one CTA per SM by shared memory).  A spin limit turns a lost barrier
+// into an error flag instead of a hang.
+//
+// Determinism: static contiguous tile ranges per CTA, fixed-order two-stage reductions, as in the
+// unfused kernels (bit-reproducible per GPU count).
+#pragma once
+
+#include "kernels_cgs_tma.cuh"
+
+namespace b2a {
+
+constexpr unsigned long long kGridSpinLimit = 1ull << 24;  // ~10 s of polling; then flag an error
+
+__device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// generic-proxy writes (st.global of the new v) -> later async-proxy reads (TMA loads of the same rows)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+template <class T> __device__ __forceinline__ T ld_cg(const T *p);
+template <> __device__ __forceinline__ double ld_cg<double>(const double *p) { return __ldcg(p); }
+template <> __device__ __forceinline__ cdouble ld_cg<cdouble>(const cdouble *p) { return __ldcg(p); }
+
+// Grid-wide reduction + barrier.  Every thread of every CTA calls it.  Per-CTA partial sums go to
+// `partials`; the CTA that arrives last sums them in a fixed order into hout / nrm2_out, (multi-GPU)
+// all-reduces the result over NVLink peer memory, and releases the grid by publishing `epoch`.
+template <class T, int CPW>
+__device__ __forceinline__ void sweep_reduce_barrier(T (&acc)[CPW], double nacc, bool have_cols, int ncols, int warp,
+                                                     int lane, T *partials, T *hout, double *nrm2_out,
+                                                     unsigned int *ticket, unsigned long long *flag,
+                                                     unsigned long long epoch, int *is_last_smem, int *error,
+                                                     const PeerView &pv) {
+  const int grid = gridDim.x;
+  if (warp < kTmaConsumerWarps) {
+    if (have_cols) {
+#pragma unroll
+      for (int i = 0; i < CPW; ++i) {
+        const int c = warp + i * kTmaConsumerWarps;
+        const T s = warp_sum(acc[i]);
+        if (lane == 0 && c < ncols) partials[(int64_t)c * grid + blockIdx.x] = s;
+      }
+    }
+    if (warp == 0) {  // nacc: already combined into warp 0 by the caller
+      const double s = warp_sum(nacc);
+      if (lane == 0) partials[(int64_t)ncols * grid + blockIdx.x] = Scalar<T>::from_real(s);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) *is_last_smem = (atomicAdd(ticket, 1u) == (unsigned)grid - 1u);
+  __syncthreads();
+  if (*is_last_smem) {
+    __threadfence();
+    const int c_lo = have_cols ? 0 : ncols;
+    for (int c = c_lo + warp; c <= ncols; c += kTmaConsumerWarps + 1) {
+      T s = Scalar<T>::zero();
+      const T *p = partials + (int64_t)c * grid;
+      for (int b = lane; b < grid; b += 32) s = Scalar<T>::add(s, ld_cg<T>(p + b));
+      s = warp_sum(s);
+      if (lane == 0) {
+        if (c < ncols)
+          hout[c] = s;
+        else
+          *nrm2_out = *reinterpret_cast<const double *>(&s);
+      }
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+    if (pv.P > 1) {
+      // [h | nrm2] is contiguous by construction (hb1 / hb2 layout): one all-reduce over peer memory
+      __syncthreads();
+      if (warp == 0) {
+        double *vals = have_cols ? reinterpret_cast<double *>(hout) : nrm2_out;
+        const int cnt = (have_cols ? ncols * (int)(sizeof(T) / sizeof(double)) : 0) + 1;
+        peer_allreduce_warp(pv, vals, cnt);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      st_release_gpu(flag, epoch);
+    }
+  }
+  if (threadIdx.x == 0) {
+    unsigned long long spins = 0;
+    while (ld_acquire_gpu(flag) < epoch) {
+      if (++spins > kGridSpinLimit) {
+        *error = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+template <class T, int CPW>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+    cgs_sweep_tma_kernel(const __grid_constant__ CUtensorMap tmap, T *__restrict__ v, int64_t n, int ncols, TmaGeom g,
+                         T *__restrict__ partials, T *__restrict__ h1, T *__restrict__ h2, double *rsq_p,
+                         double *w1sq_p, double *w2sq_p, T *__restrict__ Hcol, int *info_col, SweepState *state,
+                         unsigned long long *flag, unsigned long long epoch, int step,
+                         const __grid_constant__ PeerView pv, int64_t row_offset, int push) {
+  extern __shared__ __align__(128) unsigned char tma_smem_raw[];
+  TmaSmem *sm = reinterpret_cast<TmaSmem *>(tma_smem_raw);
+  T *hs = reinterpret_cast<T *>(tma_smem_raw + 256);  // kTmaMaxCols coefficients
+  T *ring = hs + kTmaMaxCols;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool producer_warp = warp == kTmaConsumerWarps;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap);
+    for (int s = 0; s < g.stages; ++s) {
+      mbar_init(&sm->full[s], 1);
+      mbar_init(&sm->empty[s], kTmaConsumerWarps);
+    }
+    mbar_fence_init();
+  }
+  pdl_wait();
+  if (state->poison) return;
+  __syncthreads();
+
+  const int S = g.stages;
+  const int first = blockIdx.x * g.tiles_per_cta;
+  const int ntl = my_tile_count(g, blockIdx.x);
+  const int keep = min(S, ntl);  // tiles that stay in the ring across a phase change
+  const size_t stage_elems = (size_t)(ncols + 1) * g.RT;
+  const uint32_t stage_bytes = (uint32_t)(stage_elems * sizeof(T));
+  constexpr int kInnerPerRow = sizeof(T) / sizeof(double);
+  uint32_t cmask = 0;  // consumer: parity of the next fill of each slot it has not yet observed
+  uint32_t pmask = 0;  // producer: parity of the number of fills issued per slot
+
+  // producer (one thread): fill slot l % S with local tile l once its previous content has been released
+  auto produce = [&](int l) {
+    const int s = l % S;
+    mbar_wait(&sm->empty[s], ((pmask >> s) & 1u) ^ 1u);  // first fill of a slot passes immediately
+    pmask ^= 1u << s;
+    mbar_expect_tx(&sm->full[s], stage_bytes);
+    tma_load_2d(ring + (size_t)s * stage_elems, &tmap, (first + l) * g.RT * kInnerPerRow, 0, &sm->full[s]);
+  };
+  // consumer: tile l is either still resident from the previous phase or arrives through its full barrier
+  auto acquire = [&](int l, bool resident) -> T * {
+    const int s = l % S;
+    if (!resident) {
+      mbar_wait(&sm->full[s], (cmask >> s) & 1u);
+      cmask ^= 1u << s;
+    }
+    return ring + (size_t)s * stage_elems;
+  };
+  auto release = [&](int l) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm->empty[l % S]);
+  };
+  // per-warp row partials of ||v||^2 -> warp 0, in warp order (deterministic)
+  auto combine_norm = [&](double nacc) -> double {
+    nacc = warp_sum(nacc);
+    if (lane == 0) sm->wnorm[warp] = nacc;
+    consumer_bar_sync();
+    double r = 0.0;
+    if (warp == 0 && lane == 0) {
+#pragma unroll
+      for (int w = 0; w < kTmaConsumerWarps; ++w) r += sm->wnorm[w];
+    }
+    consumer_bar_sync();  // wnorm[] may be rewritten by the next phase
+    return r;
+  };
+  // v[rows of tile] -= tile * hs, lane = row; returns the partial of ||v_new||^2
+  auto update_rows = [&](T *tile, T *xt, int64_t r0, bool write_back) -> double {
+    double part = 0.0;
+    for (int rr = warp * 32 + lane; rr < g.RT; rr += kTmaConsumerWarps * 32) {
+      T x0 = xt[rr];
+      T x1 = Scalar<T>::zero();
+      int c = 0;
+      for (; c + 2 <= ncols; c += 2) {
+        x0 = Scalar<T>::fnma(tile[(size_t)c * g.RT + rr], hs[c], x0);
+        x1 = Scalar<T>::fnma(tile[(size_t)(c + 1) * g.RT + rr], hs[c + 1], x1);
+      }
+      if (c < ncols) x0 = Scalar<T>::fnma(tile[(size_t)c * g.RT + rr], hs[c], x0);
+      x0 = Scalar<T>::add(x0, x1);
+      v[r0 + rr] = x0;
+      if (write_back) xt[rr] = x0;
+      part += Scalar<T>::abs2(x0);
+    }
+    return part;
+  };
+
+  T acc[CPW];
+#pragma unroll
+  for (int i = 0; i < CPW; ++i) acc[i] = Scalar<T>::zero();
+  double nacc = 0.0;
+
+  // ------------------------------------------------------------------ P1: h = V' v, rnorm^2 (forward)
+  if (producer_warp) {
+    if (lane == 0)
+      for (int l = 0; l < ntl; ++l) produce(l);
+  } else {
+    for (int l = 0; l < ntl; ++l) {
+      const T *tile = acquire(l, false);
+      tile_dots<T, CPW>(tile, tile + (size_t)ncols * g.RT, g.RT, ncols, warp, lane, acc, nacc, warp == 0);
+      if (l < ntl - keep) release(l);  // the last `keep` tiles stay on chip for P2
+    }
+  }
+  __syncwarp();
+  sweep_reduce_barrier<T, CPW>(acc, nacc, true, ncols, warp, lane, partials, h1, rsq_p, &state->ticket[2], flag,
+                               epoch + 1, &sm->is_last, &state->error, pv);
+  for (int c = threadIdx.x; c < ncols; c += blockDim.x) hs[c] = ld_cg<T>(h1 + c);
+  __syncthreads();
+
+  // ------------------------------------------- P2: v -= V h, wnorm^2, speculative c = V' v_new (backward)
+#pragma unroll
+  for (int i = 0; i < CPW; ++i) acc[i] = Scalar<T>::zero();
+  nacc = 0.0;
+  if (producer_warp) {
+    if (lane == 0)
+      for (int l = ntl - 1 - keep; l >= 0; --l) produce(l);
+  } else {
+    for (int l = ntl - 1; l >= 0; --l) {
+      T *tile = acquire(l, l >= ntl - keep);
+      T *xt = tile + (size_t)ncols * g.RT;
+      nacc += update_rows(tile, xt, (int64_t)(first + l) * g.RT, true);
+      consumer_bar_sync();  // the updated x tile is complete
+      double dummy = 0.0;
+      tile_dots<T, CPW>(tile, xt, g.RT, ncols, warp, lane, acc, dummy, false);
+      if (l >= keep) release(l);  // the first `keep` tiles stay on chip (with v_new in place) for P3
+    }
+    fence_proxy_async();  // P3's TMA loads read the rows of v written above
+    nacc = combine_norm(nacc);
+  }
+  __syncwarp();
+  sweep_reduce_barrier<T, CPW>(acc, nacc, true, ncols, warp, lane, partials, h2, w1sq_p, &state->ticket[3], flag,
+                               epoch + 2, &sm->is_last, &state->error, pv);
+
+  const double rsq = __ldcg(rsq_p), w1sq = __ldcg(w1sq_p);
+  double rnorm = sqrt(rsq), wnorm = sqrt(w1sq);
+  const bool second = wnorm < kEta * rnorm;  // expansion.jl:91 (strict); identical on every CTA and rank
+
+  // ------------------------------------------------------- P3 (gated): v -= V c, wnorm^2 (forward)
+  if (second) {
+    for (int c = threadIdx.x; c < ncols; c += blockDim.x) hs[c] = ld_cg<T>(h2 + c);
+    __syncthreads();
+    nacc = 0.0;
+    if (producer_warp) {
+      if (lane == 0)
+        for (int l = keep; l < ntl; ++l) produce(l);
+    } else {
+      for (int l = 0; l < ntl; ++l) {
+        T *tile = acquire(l, l < keep);
+        nacc += update_rows(tile, tile + (size_t)ncols * g.RT, (int64_t)(first + l) * g.RT, false);
+        release(l);
+      }
+      nacc = combine_norm(nacc);
+    }
+    __syncwarp();
+    sweep_reduce_barrier<T, CPW>(acc, nacc, false, ncols, warp, lane, partials, h2, w2sq_p, &state->ticket[4], flag,
+                                 epoch + 3, &sm->is_last, &state->error, pv);
+    rnorm = wnorm;
+    wnorm = sqrt(__ldcg(w2sq_p));
+  }
+
+  // --------------------------------------- P4: H column, breakdown test, normalisation (expansion.jl:95-107)
+  const bool breakdown = wnorm <= kEta * rnorm;  // expansion.jl:99 (non-strict)
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
+      const T a = ld_cg<T>(h1 + c);
+      Hcol[c] = second ? Scalar<T>::add(a, ld_cg<T>(h2 + c)) : a;  // expansion.jl:95
+    }
+    if (threadIdx.x == 0) {
+      Hcol[ncols] = Scalar<T>::from_real(breakdown ? 0.0 : wnorm);  // expansion.jl:100,104
+      info_col[0] = (second ? 1 : 0) | (breakdown ? 2 : 0);
+      if (second) atomicAdd(&state->second_passes, 1ull);
+      if (breakdown) state->poison = step;
+    }
+  }
+  if (breakdown) return;
+
+  constexpr int PV = Scalar<T>::per_vec;
+  const int64_t rb = (int64_t)first * g.RT;
+  const int64_t re = rb + (int64_t)ntl * g.RT;  // <= ld: rows past n are the zero padding of the workspace
+  const bool do_push = push && pv.P > 1;
+  const bool vec_ok = PV == 1 || (row_offset & 1) == 0;
+  for (int64_t r = rb + (int64_t)threadIdx.x * PV; r < re; r += (int64_t)blockDim.x * PV) {
+    double2 x = *reinterpret_cast<const double2 *>(v + r);
+    x.x /= wnorm;  // v ./= wnorm (expansion.jl:106): a true division, like the reference
+    x.y /= wnorm;
+    *reinterpret_cast<double2 *>(v + r) = x;
+    if (do_push && r < n) {
+      for (int p = 0; p < pv.P; ++p) {
+        T *pxb = reinterpret_cast<T *>(pv.peer[p] + pv.off_x) + row_offset;
+        if (vec_ok && (PV == 1 || r + 1 < n)) {
+          *reinterpret_cast<double2 *>(pxb + r) = x;
+        } else {
+          reinterpret_cast<double *>(pxb + r)[0] = x.x;
+          if (r + 1 < n) reinterpret_cast<double *>(pxb + r)[1] = x.y;
+        }
+      }
+    }
+  }
+  pdl_trigger();
+  if (do_push) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) sm->is_last = (atomicAdd(&state->ticket[5], 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (sm->is_last && threadIdx.x == 0) {
+      state->ticket[5] = 0u;
+      peer_x_publish(pv);
+    }
+  }
+}
+
+}  // namespace b2a

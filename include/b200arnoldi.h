@@ -96,7 +96,9 @@ enum b2a_kernel_kind {
   B2A_K_FINISH = 3, /* cgs_finish (H column, v ./= wnorm)    bytes/launch = 2 n s        */
   B2A_K_ROTATE = 4, /* in-place V <- V Q                                                 */
   B2A_K_FILL = 5,   /* counter-based rand!                                               */
-  B2A_K_COUNT = 6
+  B2A_K_SWEEP = 6,  /* fused orthogonalisation (dots + update [+ update] + finish in one
+                       persistent kernel)     bytes/launch = (2j+5) n s [+ (j+2) n s]   */
+  B2A_K_COUNT = 7
 };
 int b2a_ctx_profile_enable(b2a_ctx *ctx, int on); /* also resets the accumulators */
 int b2a_ctx_profile_get(b2a_ctx *ctx, int kind, int64_t *launches, double *ms, double *bytes);
