@@ -290,6 +290,8 @@ struct b2a_ws {
   int fused_sweep = 0;
   unsigned long long *sweep_flag = nullptr;  // release flag of the in-kernel grid barriers (monotone epoch)
   unsigned long long sweep_epoch = 0;
+  int sweep_early_trigger = 0;               // experiment (B2A_SWEEP_TRIGGER=1)
+  unsigned long long *sweep_trace = nullptr;  // per-CTA phase timestamps of the last fused launch (B2A_SWEEP_TRACE=1)
   int x_pushed_col = -1;  // 0-based column whose normalised content currently sits in every rank's x buffer
   int tune_rt_dots = 0, tune_rt_upd = 0, tune_stages = 0, tune_ctas = 1, tune_l2promo = 2;  // experiment overrides (env)
 };
@@ -597,7 +599,8 @@ static int launch_sweep_inst(b2a_ws *ws, int j, int step, const b2a::TmaGeom &g,
   ws->sweep_epoch += 4;
   CUDA_TRY(launch_pdl(kern, (unsigned)grid, (unsigned)b2a::kTmaThreads, smem, ctx->stream, tm, v, ws->n_local, j, g,
                       reinterpret_cast<DT *>(ws->partials), h1, h2, rsq, w1sq, ws->w2sq, Hcol, ws->dinfo + j, ws->state,
-                      ws->sweep_flag, epoch, step, ws->peer, ws->row_offset, push));
+                      ws->sweep_flag, epoch, step, ws->peer, ws->row_offset, push, ws->sweep_early_trigger,
+                      ws->sweep_trace));
   prof_end(ctx);
   ctx->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -1936,6 +1939,7 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
   if (const char *e = getenv("B2A_PEER_X")) ws->peer_x = e[0] != '0';
   if (const char *e = getenv("B2A_PUSH_SEPARATE")) ws->push_separate = e[0] == '1';
   if (const char *e = getenv("B2A_FUSED_SWEEP")) ws->fused_sweep = std::max(0, std::min(2, atoi(e)));
+  if (const char *e = getenv("B2A_SWEEP_TRIGGER")) ws->sweep_early_trigger = e[0] == '1';
   if (const char *e = getenv("B2A_TMA_L2PROMO")) ws->tune_l2promo = std::max(0, std::min(3, atoi(e)));
   CUDA_TRY(dev_alloc(ctx, &ws->dV, (size_t)ws->ld * m1 * es));
   CUDA_TRY(cudaMemsetAsync(ws->dV, 0, (size_t)ws->ld * m1 * es, ctx->stream));  // padding rows stay zero forever
@@ -1960,6 +1964,8 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
   const size_t o_state = carve(sizeof(b2a::SweepState));
   const size_t o_dQ = carve((size_t)std::max(maxdim * maxdim, 1) * es);
   const size_t o_flag = carve(sizeof(unsigned long long));
+  const bool want_trace = getenv("B2A_SWEEP_TRACE") && getenv("B2A_SWEEP_TRACE")[0] == '1';
+  const size_t o_trace = carve(want_trace ? sizeof(unsigned long long) * b2a::kSweepTraceSlots * ctx->num_sms : 8);
   CUDA_TRY(dev_alloc(ctx, &ws->arena, off));
   CUDA_TRY(cudaMemsetAsync(ws->arena, 0, off, ctx->stream));
   char *base = reinterpret_cast<char *>(ws->arena);
@@ -1973,6 +1979,7 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
   ws->state = reinterpret_cast<b2a::SweepState *>(base + o_state);
   ws->dQ = base + o_dQ;
   ws->sweep_flag = reinterpret_cast<unsigned long long *>(base + o_flag);
+  ws->sweep_trace = want_trace ? reinterpret_cast<unsigned long long *>(base + o_trace) : nullptr;
   const size_t want = (size_t)m1 * maxdim * es + sizeof(int) * (m1 + 1) + sizeof(b2a::SweepState) + 64;
   CUDA_TRY(pinned_get(ctx, want, &ws->pinned, &ws->pinned_bytes));
   B2A_TRY(peer_setup(ctx, ws));
@@ -2023,6 +2030,17 @@ int b2a_ws_set_col_device(b2a_ws *ws, int j, const void *dev) {
   CUDA_TRY(cudaMemcpyAsync(dst, dev, (size_t)ws->n_local * ws->esz, cudaMemcpyDeviceToDevice, ws->ctx->stream));
   return B2A_OK;
 }
+int b2a_ws_debug_sweep_trace(b2a_ws *ws, unsigned long long *out, int max_ctas, int *slots) {
+  if (!ws || !out || !slots) return fail(B2A_ERR_ARGUMENT, "NULL argument");
+  *slots = b2a::kSweepTraceSlots;
+  if (!ws->sweep_trace) return fail(B2A_ERR_ARGUMENT, "workspace was created without B2A_SWEEP_TRACE=1");
+  const int nc = std::min(max_ctas, ws->ctx->num_sms);
+  CUDA_TRY(cudaStreamSynchronize(ws->ctx->stream));
+  CUDA_TRY(cudaMemcpy(out, ws->sweep_trace, sizeof(unsigned long long) * b2a::kSweepTraceSlots * nc,
+                      cudaMemcpyDeviceToHost));
+  return B2A_OK;
+}
+
 int b2a_ws_get_cols(b2a_ws *ws, int j0, int ncols, void *host, int64_t ld) {
   if (ncols == 0) return B2A_OK;
   WS_COL_CHECK(ws, j0);

@@ -27,6 +27,12 @@
 
 namespace b2a {
 
+constexpr int kSweepTraceSlots = 8;  // start, P1 end, A done, P2 end, B done, P3 end, C done, end
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 constexpr unsigned long long kGridSpinLimit = 1ull << 24;  // ~10 s of polling; then flag an error
 
 __device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v) {
@@ -121,10 +127,15 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
                          T *__restrict__ partials, T *__restrict__ h1, T *__restrict__ h2, double *rsq_p,
                          double *w1sq_p, double *w2sq_p, T *__restrict__ Hcol, int *info_col, SweepState *state,
                          unsigned long long *flag, unsigned long long epoch, int step,
-                         const __grid_constant__ PeerView pv, int64_t row_offset, int push) {
+                         const __grid_constant__ PeerView pv, int64_t row_offset, int push, int early_trigger,
+                         unsigned long long *trace) {
   extern __shared__ __align__(128) unsigned char tma_smem_raw[];
   TmaSmem *sm = reinterpret_cast<TmaSmem *>(tma_smem_raw);
   T *hs = reinterpret_cast<T *>(tma_smem_raw + 256);  // kTmaMaxCols coefficients
+  // optional phase trace (B2A_SWEEP_TRACE=1): globaltimer of thread 0 of every CTA at the phase boundaries
+  auto mark = [&](int k) {
+    if (trace && threadIdx.x == 0) trace[(size_t)blockIdx.x * kSweepTraceSlots + k] = globaltimer_ns();
+  };
   T *ring = hs + kTmaMaxCols;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool producer_warp = warp == kTmaConsumerWarps;
@@ -140,6 +151,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   pdl_wait();
   if (state->poison) return;
   __syncthreads();
+  mark(0);
 
   const int S = g.stages;
   const int first = blockIdx.x * g.tiles_per_cta;
@@ -222,8 +234,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     }
   }
   __syncwarp();
+  mark(1);
   sweep_reduce_barrier<T, CPW>(acc, nacc, true, ncols, warp, lane, partials, h1, rsq_p, &state->ticket[2], flag,
                                epoch + 1, &sm->is_last, &state->error, pv);
+  mark(2);
   for (int c = threadIdx.x; c < ncols; c += blockDim.x) hs[c] = ld_cg<T>(h1 + c);
   __syncthreads();
 
@@ -248,8 +262,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     nacc = combine_norm(nacc);
   }
   __syncwarp();
+  mark(3);
   sweep_reduce_barrier<T, CPW>(acc, nacc, true, ncols, warp, lane, partials, h2, w1sq_p, &state->ticket[3], flag,
                                epoch + 2, &sm->is_last, &state->error, pv);
+  mark(4);
 
   const double rsq = __ldcg(rsq_p), w1sq = __ldcg(w1sq_p);
   double rnorm = sqrt(rsq), wnorm = sqrt(w1sq);
@@ -272,8 +288,10 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       nacc = combine_norm(nacc);
     }
     __syncwarp();
+    mark(5);
     sweep_reduce_barrier<T, CPW>(acc, nacc, false, ncols, warp, lane, partials, h2, w2sq_p, &state->ticket[4], flag,
                                  epoch + 3, &sm->is_last, &state->error, pv);
+    mark(6);
     rnorm = wnorm;
     wnorm = sqrt(__ldcg(w2sq_p));
   }
@@ -293,6 +311,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     }
   }
   if (breakdown) return;
+  if (early_trigger) pdl_trigger();  // let the next mat-vec's CTAs queue up behind the (light) normalisation
 
   constexpr int PV = Scalar<T>::per_vec;
   const int64_t rb = (int64_t)first * g.RT;
@@ -316,6 +335,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
       }
     }
   }
+  mark(7);
   pdl_trigger();
   if (do_push) {
     __threadfence_system();

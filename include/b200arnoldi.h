@@ -157,6 +157,10 @@ int b2a_ws_set_col(b2a_ws *ws, int j, const void *host);
 int b2a_ws_set_col_device(b2a_ws *ws, int j, const void *dev);
 /* copy columns j0 .. j0+ncols-1 (1-based) of V to a host matrix with leading dim ld */
 int b2a_ws_get_cols(b2a_ws *ws, int j0, int ncols, void *host, int64_t ld);
+/* diagnostics: per-CTA phase timestamps (ns, %globaltimer) of the last fused orthogonalisation kernel
+ * (csrc/kernels_cgs_sweep.cuh); only for workspaces created with B2A_SWEEP_TRACE=1 in the environment.
+ * out receives min(max_ctas, #SMs) x *slots values. */
+int b2a_ws_debug_sweep_trace(b2a_ws *ws, unsigned long long *out, int max_ctas, int *slots);
 /* device pointer of column j (1-based) and the leading dimension (elements) */
 int b2a_ws_col_ptr(b2a_ws *ws, int j, void **dev, int64_t *ld);
 /* host H / Q of the workspace (column-major, leading dims returned) */
