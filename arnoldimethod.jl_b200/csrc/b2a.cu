@@ -291,6 +291,7 @@ struct b2a_ws {
   unsigned long long *sweep_flag = nullptr;  // release flag of the in-kernel grid barriers (monotone epoch)
   unsigned long long sweep_epoch = 0;
   int sweep_early_trigger = 0;               // experiment (B2A_SWEEP_TRIGGER=1)
+  int sweep_pdl = 0;  // bit 0: fused sweep launched with the PDL attribute, bit 1: the mat-vec after it (B2A_SWEEP_PDL)
   unsigned long long *sweep_trace = nullptr;  // per-CTA phase timestamps of the last fused launch (B2A_SWEEP_TRACE=1)
   int x_pushed_col = -1;  // 0-based column whose normalised content currently sits in every rank's x buffer
   int tune_rt_dots = 0, tune_rt_upd = 0, tune_stages = 0, tune_ctas = 1, tune_l2promo = 2;  // experiment overrides (env)
@@ -309,6 +310,15 @@ namespace eng {
 
 // Launch with the programmatic-stream-serialization attribute (PDL, see device_common.cuh).
 static bool g_pdl = !(getenv("B2A_PDL") && getenv("B2A_PDL")[0] == '0');
+// Scoped override: launches around the fused sweep kernel are plain stream-ordered launches.  Measured on B200
+// (tools/sweepbench.py, cfg 2): with the attribute 240 us per Arnoldi step, without 227 us - the persistent
+// sweep kernel gains nothing from an early launch and loses when its CTAs or the next mat-vec's are scheduled early.
+static bool g_pdl_off = false;
+struct PdlScope {
+  bool saved;
+  explicit PdlScope(bool off) : saved(g_pdl_off) { g_pdl_off = g_pdl_off || off; }
+  ~PdlScope() { g_pdl_off = saved; }
+};
 template <class... KArgs, class... Args>
 static cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
                               Args &&...args) {
@@ -321,7 +331,7 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned bl
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl ? 1 : 0;
+  cfg.numAttrs = (g_pdl && !g_pdl_off) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
@@ -571,14 +581,20 @@ static int launch_update_tma(b2a_ws *ws, int ncols, DT *v, const DT *h, DT *cout
 }
 
 // ---- fused orthogonalisation: S1 -> S2 -> [S3] -> finish in ONE persistent kernel (kernels_cgs_sweep.cuh) ----
+static bool fused_sweep_on(const b2a_ws *ws) {
+  return ws->use_tma && ws->tune_ctas == 1 && ws->ctx->num_sms <= b2a::kSweepPartStride &&
+         (ws->fused_sweep >= 2 || (ws->fused_sweep == 1 && ws->peer.P == 1 && ws->ctx->world == 1));
+}
+
 template <class DT, int CPW>
 static int launch_sweep_inst(b2a_ws *ws, int j, int step, const b2a::TmaGeom &g, size_t smem, int grid, int push) {
   auto kern = b2a::cgs_sweep_tma_kernel<DT, CPW>;
   static bool attr_done = false;
   if (!attr_done) {
-    B2A_TRY(set_smem_attr(kern, smem));
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBudget + 2048));
     attr_done = true;
   }
+  PdlScope pdl_scope(!(ws->sweep_pdl & 1));
   CUtensorMap tm;
   if (!make_panel_tmap(ws, j, g.RT, &tm)) return fail(B2A_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   b2a_ctx *ctx = ws->ctx;
@@ -614,6 +630,8 @@ template <class DT> static int launch_sweep(b2a_ws *ws, int j, int step, int pus
   int grid;
   if (!tma_geometry(ws, j, sizeof(DT), true, false, &g, &smem, &grid)) return 1;
   if (grid > ws->ctx->num_sms) return 1;  // the in-kernel grid barrier needs every CTA resident
+  // same ring as the update kernel, larger header (two coefficient buffers instead of one)
+  smem = smem - (256 + b2a::kTmaMaxCols * sizeof(DT)) + b2a::sweep_header_bytes<DT>();
   switch (std::max(1, (j + 7) / 8)) {
     case 1: return launch_sweep_inst<DT, 1>(ws, j, step, g, smem, grid, push);
     case 2: return launch_sweep_inst<DT, 2>(ws, j, step, g, smem, grid, push);
@@ -650,8 +668,7 @@ template <class DT> static int enqueue_cgs(b2a_ws *ws, int j, int mode, int step
   // multi-GPU: the TMA kernels finish their own all-reduce over NVLink peer memory (peer_comm.cuh);
   // otherwise a host-launched NCCL all-reduce follows each reduction kernel
   const bool fused = tma && ws->peer.P > 1;
-  if (mode == 0 && j >= 1 && tma && ws->tune_ctas == 1 &&
-      (ws->fused_sweep >= 2 || (ws->fused_sweep == 1 && ws->peer.P == 1 && ctx->world == 1))) {
+  if (mode == 0 && j >= 1 && tma && fused_sweep_on(ws)) {
     // the whole orthogonalisation as one persistent kernel with in-kernel grid barriers
     const int push = (ws->peer.P > 1 && ws->peer_x && !ws->push_separate) ? 1 : 0;
     const int s = launch_sweep<DT>(ws, j, step, push);
@@ -838,6 +855,7 @@ template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, 
     }
     x = xf;
   }
+  PdlScope pdl_scope(fused_sweep_on(ws) && !(ws->sweep_pdl & 2));
   prof_begin(ctx, B2A_K_SPMV, op_bytes(A));
   if (A->kind == OP_CSC_SCATTER) {
     b2a::zero_vector_kernel<DT><<<(unsigned)std::min<int64_t>(ctx->num_sms * 8, std::max<int64_t>(1, cdiv(A->n_local, 256))), 256, 0, ctx->stream>>>(y, A->n_local, poison);
@@ -1940,6 +1958,7 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
   if (const char *e = getenv("B2A_PUSH_SEPARATE")) ws->push_separate = e[0] == '1';
   if (const char *e = getenv("B2A_FUSED_SWEEP")) ws->fused_sweep = std::max(0, std::min(2, atoi(e)));
   if (const char *e = getenv("B2A_SWEEP_TRIGGER")) ws->sweep_early_trigger = e[0] == '1';
+  if (const char *e = getenv("B2A_SWEEP_PDL")) ws->sweep_pdl = atoi(e) & 3;
   if (const char *e = getenv("B2A_TMA_L2PROMO")) ws->tune_l2promo = std::max(0, std::min(3, atoi(e)));
   CUDA_TRY(dev_alloc(ctx, &ws->dV, (size_t)ws->ld * m1 * es));
   CUDA_TRY(cudaMemsetAsync(ws->dV, 0, (size_t)ws->ld * m1 * es, ctx->stream));  // padding rows stay zero forever

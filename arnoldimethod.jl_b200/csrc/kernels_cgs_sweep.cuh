@@ -50,58 +50,106 @@ template <class T> __device__ __forceinline__ T ld_cg(const T *p);
 template <> __device__ __forceinline__ double ld_cg<double>(const double *p) { return __ldcg(p); }
 template <> __device__ __forceinline__ cdouble ld_cg<cdouble>(const cdouble *p) { return __ldcg(p); }
 
-// Grid-wide reduction + barrier.  Every thread of every CTA calls it.  Per-CTA partial sums go to
-// `partials`; the CTA that arrives last sums them in a fixed order into hout / nrm2_out, (multi-GPU)
-// all-reduces the result over NVLink peer memory, and releases the grid by publishing `epoch`.
+constexpr int kSweepPartStride = 160;  // row stride of the per-CTA partial sums (>= #SMs, multiple of 32)
+constexpr int kSweepCoefs = kTmaMaxCols + 2;  // coefficient vector + its squared norm, per buffer
+
+template <class T> __host__ __device__ constexpr size_t sweep_header_bytes() {
+  return 256 + (2 * kSweepCoefs * sizeof(T) + 127) / 128 * 128;  // TmaSmem | ha | hb, ring 128-byte aligned
+}
+
+// Grid-wide reduction + barrier.  Every thread of every CTA calls it.  Per-CTA partial sums of the columns
+// [c_lo, ncols) and of the squared norm (row `ncols`) go to `partials`; after the barrier red[c] (shared
+// memory of every CTA) holds the grid-wide sums, red[ncols] the squared norm.
+//   single GPU: the CTA that arrives last publishes `epoch`; then EVERY CTA sums the partials itself, in the
+//               same fixed order (no serial reduce-then-broadcast hop through one CTA);
+//   multi GPU : the last CTA sums, all-reduces [h | nrm2] over NVLink peer memory (peer_comm.cuh), writes the
+//               result to hout / nrm2_out and publishes `epoch`; the others fetch it from there.
 template <class T, int CPW>
 __device__ __forceinline__ void sweep_reduce_barrier(T (&acc)[CPW], double nacc, bool have_cols, int ncols, int warp,
-                                                     int lane, T *partials, T *hout, double *nrm2_out,
+                                                     int lane, T *partials, T *red, T *hout, double *nrm2_out,
                                                      unsigned int *ticket, unsigned long long *flag,
                                                      unsigned long long epoch, int *is_last_smem, int *error,
                                                      const PeerView &pv) {
   const int grid = gridDim.x;
+  const int c_lo = have_cols ? 0 : ncols;
   if (warp < kTmaConsumerWarps) {
     if (have_cols) {
 #pragma unroll
       for (int i = 0; i < CPW; ++i) {
         const int c = warp + i * kTmaConsumerWarps;
         const T s = warp_sum(acc[i]);
-        if (lane == 0 && c < ncols) partials[(int64_t)c * grid + blockIdx.x] = s;
+        if (lane == 0 && c < ncols) partials[(size_t)c * kSweepPartStride + blockIdx.x] = s;
       }
     }
     if (warp == 0) {  // nacc: already combined into warp 0 by the caller
       const double s = warp_sum(nacc);
-      if (lane == 0) partials[(int64_t)ncols * grid + blockIdx.x] = Scalar<T>::from_real(s);
+      if (lane == 0) partials[(size_t)ncols * kSweepPartStride + blockIdx.x] = Scalar<T>::from_real(s);
     }
   }
-  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) *is_last_smem = (atomicAdd(ticket, 1u) == (unsigned)grid - 1u);
+  if (threadIdx.x == 0) {
+    __threadfence();  // cumulative: covers the partials the other threads stored before the barrier above
+    *is_last_smem = (atomicAdd(ticket, 1u) == (unsigned)grid - 1u);
+  }
   __syncthreads();
-  if (*is_last_smem) {
+  const bool last = *is_last_smem != 0;
+  const bool everyone_reduces = pv.P == 1;
+  if (everyone_reduces && last && threadIdx.x == 0) {
+    *ticket = 0u;
     __threadfence();
-    const int c_lo = have_cols ? 0 : ncols;
-    for (int c = c_lo + warp; c <= ncols; c += kTmaConsumerWarps + 1) {
-      T s = Scalar<T>::zero();
-      const T *p = partials + (int64_t)c * grid;
-      for (int b = lane; b < grid; b += 32) s = Scalar<T>::add(s, ld_cg<T>(p + b));
-      s = warp_sum(s);
-      if (lane == 0) {
-        if (c < ncols)
-          hout[c] = s;
-        else
-          *nrm2_out = *reinterpret_cast<const double *>(&s);
+    st_release_gpu(flag, epoch);
+  }
+  if (everyone_reduces || last) {
+    if (everyone_reduces && threadIdx.x == 0) {
+      unsigned long long spins = 0;
+      while (ld_acquire_gpu(flag) < epoch) {
+        if (++spins > kGridSpinLimit) {
+          *error = 1;
+          break;
+        }
       }
     }
-    if (threadIdx.x == 0) *ticket = 0u;
-    if (pv.P > 1) {
-      // [h | nrm2] is contiguous by construction (hb1 / hb2 layout): one all-reduce over peer memory
-      __syncthreads();
-      if (warp == 0) {
-        double *vals = have_cols ? reinterpret_cast<double *>(hout) : nrm2_out;
-        const int cnt = (have_cols ? ncols * (int)(sizeof(T) / sizeof(double)) : 0) + 1;
-        peer_allreduce_warp(pv, vals, cnt);
+    if (everyone_reduces) __syncthreads(); else __threadfence();
+    // rows c_lo + warp, + 9, ... ; four rows per batch so that 20 independent L2 loads are in flight per lane
+    for (int k0 = 0; c_lo + warp + (kTmaConsumerWarps + 1) * k0 <= ncols; k0 += 4) {
+      T val[4][5];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = c_lo + warp + (kTmaConsumerWarps + 1) * (k0 + q);
+#pragma unroll
+        for (int m = 0; m < 5; ++m) {
+          const int b = lane + 32 * m;
+          val[q][m] = (c <= ncols && b < grid) ? ld_cg<T>(partials + (size_t)c * kSweepPartStride + b) : Scalar<T>::zero();
+        }
       }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int c = c_lo + warp + (kTmaConsumerWarps + 1) * (k0 + q);
+        T s = val[q][0];
+#pragma unroll
+        for (int m = 1; m < 5; ++m) s = Scalar<T>::add(s, val[q][m]);
+        s = warp_sum(s);
+        if (lane == 0 && c <= ncols) red[c] = s;
+      }
+    }
+  }
+  if (everyone_reduces) {
+    __syncthreads();
+    return;
+  }
+  // ---- multi-GPU: the last CTA owns the cross-GPU all-reduce and the publication
+  if (last) {
+    __syncthreads();
+    for (int c = c_lo + threadIdx.x; c < ncols; c += blockDim.x) hout[c] = red[c];
+    if (threadIdx.x == 0) {
+      *nrm2_out = *reinterpret_cast<const double *>(&red[ncols]);
+      *ticket = 0u;
+    }
+    __syncthreads();
+    if (warp == 0) {  // [h | nrm2] is contiguous by construction (hb1 / hb2 layout)
+      double *vals = have_cols ? reinterpret_cast<double *>(hout) : nrm2_out;
+      const int cnt = (have_cols ? ncols * (int)(sizeof(T) / sizeof(double)) : 0) + 1;
+      peer_allreduce_warp(pv, vals, cnt);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -119,6 +167,9 @@ __device__ __forceinline__ void sweep_reduce_barrier(T (&acc)[CPW], double nacc,
     }
   }
   __syncthreads();
+  for (int c = c_lo + threadIdx.x; c < ncols; c += blockDim.x) red[c] = ld_cg<T>(hout + c);
+  if (threadIdx.x == 0) red[ncols] = Scalar<T>::from_real(__ldcg(nrm2_out));
+  __syncthreads();
 }
 
 template <class T, int CPW>
@@ -131,12 +182,13 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
                          unsigned long long *trace) {
   extern __shared__ __align__(128) unsigned char tma_smem_raw[];
   TmaSmem *sm = reinterpret_cast<TmaSmem *>(tma_smem_raw);
-  T *hs = reinterpret_cast<T *>(tma_smem_raw + 256);  // kTmaMaxCols coefficients
+  T *ha = reinterpret_cast<T *>(tma_smem_raw + 256);  // pass-1 coefficients h, ha[ncols] = rnorm^2
+  T *hb = ha + kSweepCoefs;                           // pass-2 coefficients c, hb[ncols] = wnorm^2, hb[last] = w2^2
+  T *ring = reinterpret_cast<T *>(tma_smem_raw + sweep_header_bytes<T>());
   // optional phase trace (B2A_SWEEP_TRACE=1): globaltimer of thread 0 of every CTA at the phase boundaries
   auto mark = [&](int k) {
     if (trace && threadIdx.x == 0) trace[(size_t)blockIdx.x * kSweepTraceSlots + k] = globaltimer_ns();
   };
-  T *ring = hs + kTmaMaxCols;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool producer_warp = warp == kTmaConsumerWarps;
 
@@ -198,7 +250,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     return r;
   };
   // v[rows of tile] -= tile * hs, lane = row; returns the partial of ||v_new||^2
-  auto update_rows = [&](T *tile, T *xt, int64_t r0, bool write_back) -> double {
+  auto update_rows = [&](T *tile, T *xt, const T *hs, int64_t r0, bool write_back) -> double {
     double part = 0.0;
     for (int rr = warp * 32 + lane; rr < g.RT; rr += kTmaConsumerWarps * 32) {
       T x0 = xt[rr];
@@ -235,11 +287,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   }
   __syncwarp();
   mark(1);
-  sweep_reduce_barrier<T, CPW>(acc, nacc, true, ncols, warp, lane, partials, h1, rsq_p, &state->ticket[2], flag,
+  sweep_reduce_barrier<T, CPW>(acc, nacc, true, ncols, warp, lane, partials, ha, h1, rsq_p, &state->ticket[2], flag,
                                epoch + 1, &sm->is_last, &state->error, pv);
   mark(2);
-  for (int c = threadIdx.x; c < ncols; c += blockDim.x) hs[c] = ld_cg<T>(h1 + c);
-  __syncthreads();
 
   // ------------------------------------------- P2: v -= V h, wnorm^2, speculative c = V' v_new (backward)
 #pragma unroll
@@ -252,7 +302,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     for (int l = ntl - 1; l >= 0; --l) {
       T *tile = acquire(l, l >= ntl - keep);
       T *xt = tile + (size_t)ncols * g.RT;
-      nacc += update_rows(tile, xt, (int64_t)(first + l) * g.RT, true);
+      nacc += update_rows(tile, xt, ha, (int64_t)(first + l) * g.RT, true);
       consumer_bar_sync();  // the updated x tile is complete
       double dummy = 0.0;
       tile_dots<T, CPW>(tile, xt, g.RT, ncols, warp, lane, acc, dummy, false);
@@ -263,18 +313,17 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   }
   __syncwarp();
   mark(3);
-  sweep_reduce_barrier<T, CPW>(acc, nacc, true, ncols, warp, lane, partials, h2, w1sq_p, &state->ticket[3], flag,
+  sweep_reduce_barrier<T, CPW>(acc, nacc, true, ncols, warp, lane, partials, hb, h2, w1sq_p, &state->ticket[3], flag,
                                epoch + 2, &sm->is_last, &state->error, pv);
   mark(4);
 
-  const double rsq = __ldcg(rsq_p), w1sq = __ldcg(w1sq_p);
+  const double rsq = *reinterpret_cast<const double *>(&ha[ncols]);
+  const double w1sq = *reinterpret_cast<const double *>(&hb[ncols]);
   double rnorm = sqrt(rsq), wnorm = sqrt(w1sq);
   const bool second = wnorm < kEta * rnorm;  // expansion.jl:91 (strict); identical on every CTA and rank
 
   // ------------------------------------------------------- P3 (gated): v -= V c, wnorm^2 (forward)
   if (second) {
-    for (int c = threadIdx.x; c < ncols; c += blockDim.x) hs[c] = ld_cg<T>(h2 + c);
-    __syncthreads();
     nacc = 0.0;
     if (producer_warp) {
       if (lane == 0)
@@ -282,27 +331,26 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     } else {
       for (int l = 0; l < ntl; ++l) {
         T *tile = acquire(l, l < keep);
-        nacc += update_rows(tile, tile + (size_t)ncols * g.RT, (int64_t)(first + l) * g.RT, false);
+        nacc += update_rows(tile, tile + (size_t)ncols * g.RT, hb, (int64_t)(first + l) * g.RT, false);
         release(l);
       }
       nacc = combine_norm(nacc);
     }
     __syncwarp();
     mark(5);
-    sweep_reduce_barrier<T, CPW>(acc, nacc, false, ncols, warp, lane, partials, h2, w2sq_p, &state->ticket[4], flag,
-                                 epoch + 3, &sm->is_last, &state->error, pv);
+    // only the norm is reduced; its result lands in the spare slot hb[kSweepCoefs - 1]
+    sweep_reduce_barrier<T, CPW>(acc, nacc, false, ncols, warp, lane, partials, hb + (kSweepCoefs - 1 - ncols), h2,
+                                 w2sq_p, &state->ticket[4], flag, epoch + 3, &sm->is_last, &state->error, pv);
     mark(6);
     rnorm = wnorm;
-    wnorm = sqrt(__ldcg(w2sq_p));
+    wnorm = sqrt(*reinterpret_cast<const double *>(&hb[kSweepCoefs - 1]));
   }
 
   // --------------------------------------- P4: H column, breakdown test, normalisation (expansion.jl:95-107)
   const bool breakdown = wnorm <= kEta * rnorm;  // expansion.jl:99 (non-strict)
   if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < ncols; c += blockDim.x) {
-      const T a = ld_cg<T>(h1 + c);
-      Hcol[c] = second ? Scalar<T>::add(a, ld_cg<T>(h2 + c)) : a;  // expansion.jl:95
-    }
+    for (int c = threadIdx.x; c < ncols; c += blockDim.x)
+      Hcol[c] = second ? Scalar<T>::add(ha[c], hb[c]) : ha[c];  // expansion.jl:95
     if (threadIdx.x == 0) {
       Hcol[ncols] = Scalar<T>::from_real(breakdown ? 0.0 : wnorm);  // expansion.jl:100,104
       info_col[0] = (second ? 1 : 0) | (breakdown ? 2 : 0);
@@ -311,26 +359,45 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     }
   }
   if (breakdown) return;
-  if (early_trigger) pdl_trigger();  // let the next mat-vec's CTAs queue up behind the (light) normalisation
+  if (early_trigger) pdl_trigger();  // experiment: let the next mat-vec's CTAs queue up behind the normalisation
 
   constexpr int PV = Scalar<T>::per_vec;
+  constexpr int U = 4;  // vectors in flight per thread
   const int64_t rb = (int64_t)first * g.RT;
   const int64_t re = rb + (int64_t)ntl * g.RT;  // <= ld: rows past n are the zero padding of the workspace
+  const int64_t stride = (int64_t)blockDim.x * PV;
   const bool do_push = push && pv.P > 1;
   const bool vec_ok = PV == 1 || (row_offset & 1) == 0;
-  for (int64_t r = rb + (int64_t)threadIdx.x * PV; r < re; r += (int64_t)blockDim.x * PV) {
-    double2 x = *reinterpret_cast<const double2 *>(v + r);
-    x.x /= wnorm;  // v ./= wnorm (expansion.jl:106): a true division, like the reference
-    x.y /= wnorm;
-    *reinterpret_cast<double2 *>(v + r) = x;
-    if (do_push && r < n) {
+  for (int64_t r0 = rb + (int64_t)threadIdx.x * PV; r0 < re; r0 += stride * U) {
+    double2 x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + u * stride;
+      x[u] = r < re ? *reinterpret_cast<const double2 *>(v + r) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      x[u].x /= wnorm;  // v ./= wnorm (expansion.jl:106): a true division, like the reference
+      x[u].y /= wnorm;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r < re) *reinterpret_cast<double2 *>(v + r) = x[u];
+    }
+    if (do_push) {
       for (int p = 0; p < pv.P; ++p) {
         T *pxb = reinterpret_cast<T *>(pv.peer[p] + pv.off_x) + row_offset;
-        if (vec_ok && (PV == 1 || r + 1 < n)) {
-          *reinterpret_cast<double2 *>(pxb + r) = x;
-        } else {
-          reinterpret_cast<double *>(pxb + r)[0] = x.x;
-          if (r + 1 < n) reinterpret_cast<double *>(pxb + r)[1] = x.y;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t r = r0 + u * stride;
+          if (r >= re || r >= n) continue;
+          if (vec_ok && (PV == 1 || r + 1 < n)) {
+            *reinterpret_cast<double2 *>(pxb + r) = x[u];
+          } else {
+            reinterpret_cast<double *>(pxb + r)[0] = x[u].x;
+            if (r + 1 < n) reinterpret_cast<double *>(pxb + r)[1] = x[u].y;
+          }
         }
       }
     }

@@ -13,14 +13,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 VARIANTS = [
     ("unfused", {}),
-    ("unfused_nopdl", {"B2A_PDL": "0"}),
     ("fused", {"B2A_FUSED_SWEEP": "1"}),
-    ("fused_nopdl", {"B2A_FUSED_SWEEP": "1", "B2A_PDL": "0"}),
-    ("fused_trigger", {"B2A_FUSED_SWEEP": "1", "B2A_SWEEP_TRIGGER": "1"}),
+    ("fused_pdl1", {"B2A_FUSED_SWEEP": "1", "B2A_SWEEP_PDL": "1"}),
+    ("fused_pdl2", {"B2A_FUSED_SWEEP": "1", "B2A_SWEEP_PDL": "2"}),
+    ("fused_pdl3", {"B2A_FUSED_SWEEP": "1", "B2A_SWEEP_PDL": "3"}),
     ("fused_rt128", {"B2A_FUSED_SWEEP": "1", "B2A_TMA_RT_UPD": "128"}),
-    ("fused_rt64", {"B2A_FUSED_SWEEP": "1", "B2A_TMA_RT_UPD": "64"}),
-    ("fused_rt128_st3", {"B2A_FUSED_SWEEP": "1", "B2A_TMA_RT_UPD": "128", "B2A_TMA_STAGES": "3"}),
-    ("unfused_rt128", {"B2A_TMA_RT_UPD": "128"}),
+    ("fused_stages3", {"B2A_FUSED_SWEEP": "1", "B2A_TMA_STAGES": "3"}),
 ]
 
 
@@ -72,6 +70,7 @@ def one():
         buf = (C.c_ulonglong * (148 * 8))()
         L.check(L.lib().b2a_ws_debug_sweep_trace(ws._h, buf, 148, C.byref(slots)))
         t = np.array(buf[:], dtype=np.float64).reshape(148, 8)
+        t = t[t[:, 0] > 0]  # CTAs that exist (the grid can be smaller than the SM count)
         t0 = t[:, 0].min()
         names = ["start", "P1_end", "A_done", "P2_end", "B_done", "P3_end", "C_done", "end"]
         out["trace_last_step_us"] = {
