@@ -285,13 +285,16 @@ struct b2a_ws {
   int finish_grid_mult = 4;
   bool push_separate = false;  // experiment: push x with its own kernel instead of inside cgs_finish
   bool peer_x = true;  // fused x push (B2A_PEER_X=0: NCCL all-gather for x, in-kernel all-reduce kept)
-  // fused orthogonalisation (kernels_cgs_sweep.cuh): 0 = four kernels per step, 1 = one persistent kernel on
-  // single-GPU workspaces, 2 = also on row-sharded ones (B2A_FUSED_SWEEP)
-  int fused_sweep = 0;
+  // fused orthogonalisation (kernels_cgs_sweep.cuh): 0 = four kernels per step, 1 (default) = one persistent
+  // kernel on single-GPU workspaces, 2 = also on row-sharded ones (B2A_FUSED_SWEEP)
+  int fused_sweep = 1;
   unsigned long long *sweep_flag = nullptr;  // release flag of the in-kernel grid barriers (monotone epoch)
   unsigned long long sweep_epoch = 0;
   int sweep_early_trigger = 0;               // experiment (B2A_SWEEP_TRIGGER=1)
-  int sweep_pdl = 0;  // bit 0: fused sweep launched with the PDL attribute, bit 1: the mat-vec after it (B2A_SWEEP_PDL)
+  // bit 0: the fused sweep is launched with the PDL attribute (its prologue overlaps the mat-vec's tail), bit 1: the
+  // mat-vec after it too (B2A_SWEEP_PDL).  Measured per Arnoldi step at cfg 2: 0 -> 216.7 us, 1 -> 214.9, 2 -> 225.2,
+  // 3 -> 222.9 (four-kernel path with PDL: 230.6)
+  int sweep_pdl = 1;
   unsigned long long *sweep_trace = nullptr;  // per-CTA phase timestamps of the last fused launch (B2A_SWEEP_TRACE=1)
   int x_pushed_col = -1;  // 0-based column whose normalised content currently sits in every rank's x buffer
   int tune_rt_dots = 0, tune_rt_upd = 0, tune_stages = 0, tune_ctas = 1, tune_l2promo = 2;  // experiment overrides (env)
@@ -310,9 +313,8 @@ namespace eng {
 
 // Launch with the programmatic-stream-serialization attribute (PDL, see device_common.cuh).
 static bool g_pdl = !(getenv("B2A_PDL") && getenv("B2A_PDL")[0] == '0');
-// Scoped override: launches around the fused sweep kernel are plain stream-ordered launches.  Measured on B200
-// (tools/sweepbench.py, cfg 2): with the attribute 240 us per Arnoldi step, without 227 us - the persistent
-// sweep kernel gains nothing from an early launch and loses when its CTAs or the next mat-vec's are scheduled early.
+// Scoped override: the mat-vec that follows a fused sweep kernel is a plain stream-ordered launch (measured on
+// B200, tools/sweepbench.py: its CTAs scheduled early behind the persistent kernel cost ~10 us per step).
 static bool g_pdl_off = false;
 struct PdlScope {
   bool saved;

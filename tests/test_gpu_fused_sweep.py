@@ -1,11 +1,14 @@
-"""GPU parity of the fused orthogonalisation kernel (kernels_cgs_sweep.cuh, B2A_FUSED_SWEEP=1):
-one persistent kernel with in-kernel grid barriers instead of the four kernels
-S1 dots / S2 update / gated S3 update / finish of src/expansion.jl:69-109.
+"""GPU parity of the two orthogonalisation paths of src/expansion.jl:69-109:
 
-The kernel-level and sweep-level tests of test_gpu_kernels.py are re-run with the fused path
-switched on (same oracle, same tolerances), the launch counter proves that the fused kernel
-really ran, and fused and unfused results are compared directly on identical inputs at sizes
-where every CTA streams many tiles (ring re-use across the phase changes).
+  B2A_FUSED_SWEEP=1 (default on one GPU): kernels_cgs_sweep.cuh, ONE persistent kernel with in-kernel
+                     grid barriers;
+  B2A_FUSED_SWEEP=0: the four kernels S1 dots / S2 update / gated S3 update / finish (still the path of
+                     row-sharded workspaces, re-seeds and panels wider than 64 columns).
+
+The kernel-level and sweep-level tests of test_gpu_kernels.py are run under BOTH settings (same oracle,
+same tolerances), the launch counter proves which path really ran, and the two paths are compared
+directly on identical inputs at sizes where every CTA streams many tiles (ring re-use across the
+phase changes of the fused kernel).
 """
 
 import numpy as np
@@ -26,9 +29,10 @@ def ctx():
     return b2a.default_context()
 
 
-@pytest.fixture(autouse=True)
-def fused(monkeypatch):
-    monkeypatch.setenv("B2A_FUSED_SWEEP", "1")
+@pytest.fixture(autouse=True, params=["1", "0"], ids=["fused", "four_kernels"])
+def fused(request, monkeypatch):
+    monkeypatch.setenv("B2A_FUSED_SWEEP", request.param)
+    return request.param
 
 
 def _orth(ctx, T, Vp, v, fused_on, monkeypatch):
@@ -49,9 +53,11 @@ def _orth(ctx, T, Vp, v, fused_on, monkeypatch):
 
 @pytest.mark.parametrize("T", TYPES)
 @pytest.mark.parametrize("n,j", [(777, 3), (40_000, 9), (300_000, 24), (1_000_000, 40)])
-def test_fused_equals_unfused(ctx, monkeypatch, T, n, j):
+def test_fused_equals_unfused(ctx, fused, monkeypatch, T, n, j):
     """Same inputs through both paths: one launch instead of four, identical decisions, h and v equal
     up to the summation order (the two paths tile the rows differently)."""
+    if fused == "0":
+        pytest.skip("direct comparison: runs both paths itself")
     if T is np.complex128 and n > 500_000:
         n = 500_000
     rng = np.random.default_rng(100 + j)
@@ -123,7 +129,7 @@ def test_partialschur_fused_vs_oracle(ctx, T):
     assert np.linalg.norm(Q.conj().T @ Q - np.eye(Q.shape[1])) < 1000 * K.EPS
 
 
-def test_fused_bench_shape_sweep(ctx):
+def test_fused_bench_shape_sweep(ctx, fused):
     """cfg-2 shape (n = 1e6, maxdim 40): a full sweep with the fused kernel keeps the Arnoldi relation
     (independent SciPy mat-vec) and orthonormality - size-independent properties at BASELINE's size."""
     rng = np.random.default_rng(7)
@@ -138,7 +144,8 @@ def test_fused_bench_shape_sweep(ctx):
     op = b2a.Operator.from_matrix(ctx, A)
     l0 = ctx.launches
     st = ws.iterate_arnoldi(op, 1, mx)
-    assert ctx.launches - l0 == 2 * mx  # one mat-vec + one fused sweep per Arnoldi step
+    # one mat-vec + one fused sweep per Arnoldi step (four-kernel path: mat-vec + S1 + S2 + S3 + finish)
+    assert ctx.launches - l0 == (2 if fused == "1" else 5) * mx
     assert st.matvecs == mx and st.breakdowns == 0
     V, H = ws.V, np.array(ws.H)
     assert np.linalg.norm(A @ V[:, :mx] - V @ H) < 1e-12 * np.linalg.norm(H)
