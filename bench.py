@@ -73,8 +73,13 @@ def make_v1(n_global, row_offset, n_local, seed=1):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of
-# this workload (profiles/r1_ncu_full_summary.txt); None where no capture exists
-NCU_TRAFFIC_BYTES = {"spmv": 216.4e6}
+# this workload (profiles/r1b_ncu_full_summary.txt); None where no capture exists.  The bytes of the fused
+# sweep kernel depend on j and on whether its gated phase ran, so its entry is the measured ratio
+# traffic / algorithmic bytes of the two captured launches (j = 39 without, j = 40 with second pass:
+# 568.6 / 664 MB and 830.5 / 1016 MB - below 1 because the ring is re-used across the phases and the
+# backward pass finds the tail of the panel in L2), applied to the average algorithmic bytes per launch.
+NCU_TRAFFIC_BYTES = {"spmv": 216.5e6}
+NCU_TRAFFIC_RATIO = {"cgs_sweep": 0.833}
 LIMITER_NOTES = {
     "spmv": "uniformly random columns: every 8-byte gather of x moves a 32-byte sector through L2->L1; ncu: "
             "lts__throughput 70 %, l1tex__throughput 72 % of peak, DRAM traffic == algorithmic bytes. "
@@ -347,6 +352,9 @@ def run_gpu(args):
                     "algo_bytes_per_launch": kern[top]["algo_bytes_per_launch"],
                     "avg_launch_us": kern[top]["avg_us"], "kernels": kern}
         roofline["traffic"] = NCU_TRAFFIC_BYTES.get(top)
+        if roofline["traffic"] is None and top in NCU_TRAFFIC_RATIO:
+            roofline["traffic"] = round(NCU_TRAFFIC_RATIO[top] * kern[top]["algo_bytes_per_launch"], 1)
+            roofline["traffic_source"] = "ncu ratio traffic/algorithmic of two captured launches x average algorithmic bytes"
         roofline["limiter"] = LIMITER_NOTES.get(top)
         # context: the HBM-streaming Gram-Schmidt sweeps (dots + update) taken together, and all kernels
         gs = [prof[k] for k in ("cgs_dots", "cgs_update", "cgs_sweep") if k in prof and prof[k]["launches"]]
