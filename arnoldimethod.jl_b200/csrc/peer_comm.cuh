@@ -56,8 +56,9 @@ __device__ __forceinline__ void peer_allreduce_warp(const PeerView &pv, double *
   const int lane = threadIdx.x & 31;
   unsigned long long seq = 0;
   if (lane == 0) {
-    seq = *pv.seq_ar + 1ull;
-    *pv.seq_ar = seq;
+    // atomic at L2: inside the fused sweep kernel successive all-reduces may run on different SMs, and a
+    // plain load could return a stale L1 copy of the counter
+    seq = atomicAdd(pv.seq_ar, 1ull) + 1ull;
   }
   seq = __shfl_sync(0xffffffffu, seq, 0);
   const int buf = (int)(seq % kPeerBufs);
@@ -101,8 +102,7 @@ __device__ __forceinline__ void peer_allreduce_warp(const PeerView &pv, double *
 // finishes last bumps the device counter seq_x and publishes it in every peer's flag_x[rank].
 // The consumer (SpMV) waits until all P flags reached its own seq_x.
 __device__ __forceinline__ void peer_x_publish(const PeerView &pv) {  // one thread of the last CTA
-  const unsigned long long seq = *pv.seq_x + 1ull;
-  *pv.seq_x = seq;
+  const unsigned long long seq = atomicAdd(pv.seq_x, 1ull) + 1ull;
   __threadfence_system();
   for (int p = 0; p < pv.P; ++p)
     st_release_sys(reinterpret_cast<unsigned long long *>(pv.peer[p] + pv.off_flag_x) + pv.rank, seq);
