@@ -90,6 +90,7 @@ SIGNATURES = {
     "b2a_ws_set_col": (_i, [_vp, _i, _vp]),
     "b2a_ws_set_col_device": (_i, [_vp, _i, _vp]),
     "b2a_ws_get_cols": (_i, [_vp, _i, _i, _vp, _i64]),
+    "b2a_ws_comm_mode": (_i, [_vp, _pi]),
     "b2a_ws_debug_sweep_trace": (_i, [_vp, _vp, _i, _pi]),
     "b2a_ws_col_ptr": (_i, [_vp, _i, _pvp, _pi64]),
     "b2a_ws_host_arrays": (_i, [_vp, _pvp, _pi, _pvp, _pi]),

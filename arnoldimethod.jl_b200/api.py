@@ -373,6 +373,14 @@ class ArnoldiWorkspace:
             L.check(L.lib().b2a_rotate_final(self._h, int(nconv), _ptr(Qf), Qf.shape[0], C.byref(st)))
         return st
 
+    @property
+    def comm_mode(self):
+        """'single' | 'nccl' (host-launched collectives) | 'peer' (collectives fused into the kernels over
+        NVLink peer memory; one workspace per context owns the peer block at a time)."""
+        m = C.c_int()
+        L.check(L.lib().b2a_ws_comm_mode(self._h, C.byref(m)))
+        return ("single", "nccl", "peer")[m.value]
+
     # -- BLAS-level operations of the reference's generic code (slow path: one call each)
     def norm(self, j):
         """``norm(view(V, :, j))``"""

@@ -584,8 +584,11 @@ static int launch_update_tma(b2a_ws *ws, int ncols, DT *v, const DT *h, DT *cout
 
 // ---- fused orthogonalisation: S1 -> S2 -> [S3] -> finish in ONE persistent kernel (kernels_cgs_sweep.cuh) ----
 static bool fused_sweep_on(const b2a_ws *ws) {
-  return ws->use_tma && ws->tune_ctas == 1 && ws->ctx->num_sms <= b2a::kSweepPartStride &&
-         (ws->fused_sweep >= 2 || (ws->fused_sweep == 1 && ws->peer.P == 1 && ws->ctx->world == 1));
+  if (!ws->use_tma || ws->tune_ctas != 1 || ws->ctx->num_sms > b2a::kSweepPartStride) return false;
+  if (ws->ctx->world == 1) return ws->fused_sweep >= 1;
+  // row-sharded: the kernel all-reduces inside its grid barriers, which needs the NVLink peer block (a workspace
+  // that fell back to host-launched NCCL collectives keeps the four-kernel path)
+  return ws->fused_sweep >= 2 && ws->peer.P == ws->ctx->world;
 }
 
 template <class DT, int CPW>
@@ -2051,6 +2054,12 @@ int b2a_ws_set_col_device(b2a_ws *ws, int j, const void *dev) {
   CUDA_TRY(cudaMemcpyAsync(dst, dev, (size_t)ws->n_local * ws->esz, cudaMemcpyDeviceToDevice, ws->ctx->stream));
   return B2A_OK;
 }
+int b2a_ws_comm_mode(b2a_ws *ws, int *mode) {
+  if (!ws || !mode) return fail(B2A_ERR_ARGUMENT, "NULL argument");
+  *mode = ws->ctx->world == 1 ? 0 : (ws->peer.P == ws->ctx->world ? 2 : 1);
+  return B2A_OK;
+}
+
 int b2a_ws_debug_sweep_trace(b2a_ws *ws, unsigned long long *out, int max_ctas, int *slots) {
   if (!ws || !out || !slots) return fail(B2A_ERR_ARGUMENT, "NULL argument");
   *slots = b2a::kSweepTraceSlots;

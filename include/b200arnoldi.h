@@ -157,6 +157,10 @@ int b2a_ws_set_col(b2a_ws *ws, int j, const void *host);
 int b2a_ws_set_col_device(b2a_ws *ws, int j, const void *dev);
 /* copy columns j0 .. j0+ncols-1 (1-based) of V to a host matrix with leading dim ld */
 int b2a_ws_get_cols(b2a_ws *ws, int j0, int ncols, void *host, int64_t ld);
+/* how the workspace's collectives run: 0 = single GPU, 1 = host-launched NCCL (all-reduce of h, all-gather of x),
+ * 2 = fused into the kernels over NVLink peer memory (csrc/peer_comm.cuh).  One workspace per context owns the
+ * peer block at a time; a second live workspace on the same context gets mode 1. */
+int b2a_ws_comm_mode(b2a_ws *ws, int *mode);
 /* diagnostics: per-CTA phase timestamps (ns, %globaltimer) of the last fused orthogonalisation kernel
  * (csrc/kernels_cgs_sweep.cuh); only for workspaces created with B2A_SWEEP_TRACE=1 in the environment.
  * out receives min(max_ctas, #SMs) x *slots values. */

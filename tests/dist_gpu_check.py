@@ -42,6 +42,8 @@ def main():
 
         # sweep parity: H after 15 Arnoldi steps
         ws = b2a.ArnoldiWorkspace(v1, 20, ctx=ctx)
+        if os.environ.get("B2A_NO_PEER") != "1":
+            assert ws.comm_mode == "peer", ws.comm_mode  # collectives fused into the kernels over NVLink
         op = b2a.Operator.from_matrix(ctx, A)
         ws.reinitialize(0, "keep")
         ws.iterate_arnoldi(op, 1, 15)
@@ -74,7 +76,12 @@ def main():
         assert np.linalg.norm(Q.conj().T @ Q - np.eye(Q.shape[1])) < 1e-12
         if rank == 0:
             print(f"{T.__name__}: world={world} mvproducts={hist.mvproducts} (oracle {ho.mvproducts}) "
-                  f"H err={err:.1e} ||AQ-QR||={res:.2e}", flush=True)
+                  f"H err={err:.1e} ||AQ-QR||={res:.2e} collectives={P.workspace.comm_mode} "
+                  f"fused_sweep={os.environ.get('B2A_FUSED_SWEEP', 'default')}", flush=True)
+        # the result keeps its workspace (Q is a view of V): release it so that the next workspace of this
+        # context gets the NVLink peer block again (one owner at a time; others fall back to NCCL)
+        P.workspace.close()
+        op.close()
     # breakdown under sharding (test/expansion.jl:34-55 shape): block-diagonal A, v1 = e1 -> the Krylov space is
     # invariant after 4 steps: H[5,4] == 0 exactly on every rank, the re-seeded column (global-row keyed RNG,
     # identical for every GPU count) keeps V orthonormal, and the sweep resumes
