@@ -2124,6 +2124,9 @@ template <class HT> static int orthogonalize_impl(b2a_ws *ws, int j, void *h_hos
   std::memcpy(&info, ws->pinned + (size_t)m1 * sizeof(HT), sizeof(int));
   prof_collect(ws->ctx, &info, j, 1);
   if (ok) *ok = (info & 2) ? 0 : 1;
+  int err = 0;
+  CUDA_TRY(cudaMemcpy(&err, &ws->state->error, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) return fail(B2A_ERR_CUDA, "fused orthogonalisation: grid barrier timed out");
   return B2A_OK;
 }
 

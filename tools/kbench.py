@@ -41,15 +41,13 @@ if __name__ == "__main__":
     T = np.complex128 if "--complex" in sys.argv else np.float64
     configs = [dict()]
     if "--sweep" in sys.argv:
-        configs = [dict(B2A_NO_TMA="1")]
-        configs = [dict()]
-        for ctas in (1, 2):
-            for l2 in (0, 1, 2, 3):
-                configs.append(dict(B2A_TMA_CTAS=str(ctas), B2A_TMA_L2PROMO=str(l2)))
+        configs = [dict(), dict(B2A_FUSED_SWEEP="0"), dict(B2A_NO_TMA="1", B2A_FUSED_SWEEP="0")]
+        for l2 in (0, 1, 2, 3):
+            configs.append(dict(B2A_TMA_L2PROMO=str(l2)))
         for rt in (128, 256):
-            configs.append(dict(B2A_TMA_CTAS="2", B2A_TMA_RT_DOTS=str(rt), B2A_TMA_RT_UPD=str(rt)))
+            configs.append(dict(B2A_TMA_RT_DOTS=str(rt), B2A_TMA_RT_UPD=str(rt)))
     for cfg in configs:
-        for k in ("B2A_NO_TMA", "B2A_TMA_RT_DOTS", "B2A_TMA_RT_UPD", "B2A_TMA_STAGES", "B2A_TMA_CTAS", "B2A_TMA_L2PROMO"):
+        for k in ("B2A_NO_TMA", "B2A_FUSED_SWEEP", "B2A_TMA_RT_DOTS", "B2A_TMA_RT_UPD", "B2A_TMA_STAGES", "B2A_TMA_L2PROMO"):
             os.environ.pop(k, None)
         os.environ.update(cfg)
         r = run(n, j, T)
