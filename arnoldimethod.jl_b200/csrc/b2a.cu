@@ -1478,9 +1478,29 @@ static int check_op_args(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_glo
 }
 
 // ---- column blocking -------------------------------------------------------------------------
-// Decide the number of column blocks: only when x does not fit a comfortable share of L2 AND the columns are
-// scattered (mean |col - row| far beyond an L2-sized window); banded / stencil operators are left alone.
+// Decide the number of column blocks.  Blocking pays only when
+//   (i)   x does not fit a comfortable share of L2 (> 48 MB),
+//   (ii)  the columns are scattered (mean |col - row| far beyond an L2-sized window; banded / stencil operators
+//         are left alone), and
+//   (iii) the blocks are not too many for the row density: every block re-reads the row pointers and
+//         read-modify-writes y, 8 + 2 s bytes per row and block, while the unblocked kernel over-fetches
+//         32 - s bytes per nonzero (a 32-byte sector per s-byte gather that misses L2).  Measured on a cfg-5
+//         shard (n = 1.25e7 square, 15 nnz/row, 3 blocks): 1.7x for blocking, in line with the model (72 vs 360
+//         bytes per row); the TRUE cfg-5 shard (1.25e7 rows x 1e8 columns, x = 763 MiB, 24 blocks of 32 MiB)
+//         would pay 576 bytes per row for blocking against 360 without, so it stays unblocked.
 // B2A_SPMV_BLOCK_MB: unset/-1 = automatic, 0 = never, > 0 = force blocks of that many MB of x.
+static int col_block_plan(double x_bytes, size_t es, double nnz_per_row, double mean_col_distance_bytes) {
+  if (x_bytes <= 48.0 * 1048576.0) return 1;
+  if (mean_col_distance_bytes < 8.0 * 1048576.0) return 1;
+  const double per_row_block = 8.0 + 2.0 * (double)es;
+  const double overfetch_per_row = nnz_per_row * (32.0 - (double)es);
+  for (double mb : {32.0, 48.0}) {  // 32 MB measured best (16: 1734, 24: 1358, 32: 1227, 48: 1250 us)
+    const double nb = std::ceil(x_bytes / (mb * 1048576.0));
+    if (nb * per_row_block < 0.8 * overfetch_per_row) return (int)std::min(4096.0, nb);
+  }
+  return 1;
+}
+
 extern "C++" {
 template <class RP, class CI>
 static int decide_col_blocks(RP rp, CI ci, int64_t n_rows, int64_t n_global, int64_t row_offset, size_t es) {
@@ -1499,8 +1519,8 @@ static int decide_col_blocks(RP rp, CI ci, int64_t n_rows, int64_t n_global, int
       sum += std::fabs((double)(ci(i) - (row_offset + r)));
       ++cnt;
     }
-  if (cnt == 0 || sum / (double)cnt * (double)es < 8.0 * 1048576.0) return 1;
-  return (int)std::min<double>(4096.0, std::ceil(x_bytes / (32.0 * 1048576.0)));
+  if (cnt == 0) return 1;
+  return col_block_plan(x_bytes, es, (double)rp(n_rows) / (double)n_rows, sum / (double)cnt * (double)es);
 }
 
 // Reorder the CSR entries block-major (stable counting sort by (column block, row)): bptr gets nblocks row-pointer
@@ -2456,6 +2476,13 @@ int b2a_host_sortschur(int dtype, void *H, int ldh, void *Q, int ldq, int maxdim
       for (int i = 1; i <= maxdim; ++i) Qm(i, j) = (i == j) ? cplx(1.0) : cplx(0.0);
     sortschur(Hm, Qm, nconv, Ordering{which});
   }
+  return B2A_OK;
+}
+
+int b2a_host_col_block_plan(int dtype, int64_t n_global, double nnz_per_row, double mean_col_distance, int *nblocks) {
+  if (!nblocks || n_global < 1) return fail(B2A_ERR_ARGUMENT, "bad argument");
+  const size_t es = dtype_size(dtype);
+  *nblocks = col_block_plan((double)n_global * (double)es, es, nnz_per_row, mean_col_distance * (double)es);
   return B2A_OK;
 }
 

@@ -288,6 +288,11 @@ int b2a_host_restart(int dtype, void *H, int ldh, void *Q, int ldq, int maxdim, 
 /* sortschur!(H, Q <- I, nconv, ordering) - src/run.jl:379,465-502 */
 int b2a_host_sortschur(int dtype, void *H, int ldh, void *Q, int ldq, int maxdim, int nconv, int which);
 
+/* Upload-time plan of the CSR mat-vec (no GPU needed): number of column blocks b2a_csr_create would use for an
+ * operator with n_global columns, `nnz_per_row` entries per row and a mean |column - row| of
+ * `mean_col_distance` (in elements); 1 = plain CSR.  See the cost model at col_block_plan() in csrc/b2a.cu. */
+int b2a_host_col_block_plan(int dtype, int64_t n_global, double nnz_per_row, double mean_col_distance, int *nblocks);
+
 /* givensAlgorithm(f, g) -> (c, s, r); f, g, s, r are 1 (F64) or 2 (C64) doubles */
 int b2a_host_givens(int dtype, const double *f, const double *g, double *c, double *s, double *r);
 

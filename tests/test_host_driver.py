@@ -282,3 +282,33 @@ def test_restart_sequences_clustered_symmetric():
     for seed in range(4):
         acts, purges, nconv = _restart_sequence(A, np.float64, 5, "LM", 1e-12, 10, 20, 400, seed)
         assert nconv >= 5
+
+
+# ------------------------------------------------------------------ upload-time mat-vec plan (host logic)
+def _col_blocks(dtype_code, n_global, nnz_per_row, mean_dist):
+    import ctypes as C
+
+    from arnoldimethod_jl_b200 import _lib as L
+
+    nb = C.c_int()
+    L.check(L.lib().b2a_host_col_block_plan(dtype_code, int(n_global), float(nnz_per_row), float(mean_dist), C.byref(nb)))
+    return nb.value
+
+
+def test_column_block_plan_cost_model():
+    """Column blocking of the CSR mat-vec: only for x beyond L2, scattered columns, and few enough
+    blocks for the row density (every block re-reads row pointers and read-modify-writes y)."""
+    F64, C64 = 0, 1
+    # cfg 2: x = 8 MB sits in L2 -> plain CSR
+    assert _col_blocks(F64, 1_000_000, 16, 333_000) == 1
+    # cfg 3 at full size: x = 1 GB but a 7-point stencil (mean distance ~ 512^2 * 8 B = 2 MB window) -> plain CSR
+    assert _col_blocks(F64, 512 ** 3, 7, 2 * 512 ** 2 / 7) == 1
+    # square cfg-5 shard (n = 1.25e7, x = 95 MiB, 15 random nnz/row): 3 blocks of <= 32 MiB (measured 1.7x)
+    assert _col_blocks(F64, 12_500_000, 15, 4_000_000) == 3
+    # the TRUE cfg-5 shard sees all 1e8 columns (x = 763 MiB): 24 (or 16) blocks would cost more than the
+    # sector over-fetch they save at 15 nnz/row -> stays unblocked
+    assert _col_blocks(F64, 100_000_000, 15, 33_000_000) == 1
+    # ... but a denser operator of the same order is blocked
+    assert _col_blocks(F64, 100_000_000, 64, 33_000_000) == 24
+    # cfg 4 at full size (ComplexF64, x = 80 MB, 20 nnz/row): 3 blocks
+    assert _col_blocks(C64, 5_000_000, 20, 1_600_000) == 3
