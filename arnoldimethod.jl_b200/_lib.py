@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libb200arnoldi.so")
 F64, C64 = 0, 1
 WHICH = {"LM": 0, "LR": 1, "SR": 2, "LI": 3, "SI": 4}
 INIT_NONE, INIT_RAND, INIT_KEEP = 0, 1, 2
-KERNEL_KINDS = ("spmv", "cgs_dots", "cgs_update", "cgs_finish", "rotate", "fill", "cgs_sweep")
+KERNEL_KINDS = ("spmv", "cgs_dots", "cgs_update", "cgs_finish", "rotate", "fill", "cgs_sweep", "xchg")
 OK, ERR_ARGUMENT, ERR_DIMENSION, ERR_CUDA, ERR_NCCL, ERR_OOM, ERR_QR, ERR_INTERNAL, ERR_CALLBACK = (
     0, -1, -2, -3, -4, -5, -6, -7, -8,
 )

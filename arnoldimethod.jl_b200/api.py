@@ -526,6 +526,14 @@ def partialschur(A, v1=None, nev=None, which="LM", tol=None, mindim=None, maxdim
     _which_code(which)
     if v1 is not None and np.shape(v1)[0] != n:
         raise ValueError("v1 should have the same dimension as A")
+    if v1 is not None and np.iscomplexobj(v1):
+        # the reference takes the workspace type from v1 (`ArnoldiWorkspace(v1, maxdim)`, src/run.jl:125): a complex
+        # start vector with a real A runs in ComplexF64.  Device kernels need one element type, so A is promoted.
+        if isinstance(A, Operator):
+            if A.dtype != np.complex128:
+                raise ValueError("complex v1 with a Float64 device operator: build the operator from a complex matrix")
+        elif not np.issubdtype(A.dtype, np.complexfloating):
+            A = A.astype(np.complex128)
     op, owned = _as_operator(A, ctx)
     try:
         ws = ArnoldiWorkspace(n, maxdim, dtype=op.dtype, ctx=ctx)

@@ -32,8 +32,10 @@
 #include "host_dense.hpp"
 #include "kernels_cgs.cuh"
 #include "kernels_cgs_tma.cuh"
+#include "kernels_blocks.cuh"
 #include "kernels_cgs_sweep.cuh"
 #include "kernels_rotate.cuh"
+#include "kernels_rotate_mma.cuh"
 #include "kernels_spmv.cuh"
 #include "kernels_spmv_tma.cuh"
 #include "peer_comm.cuh"
@@ -148,6 +150,15 @@ struct b2a_ctx {
   int peer_slot = 0;
   size_t peer_x_bytes = 0;
   bool peer_busy = false;    // handed to a live workspace
+  // staged x exchange (row-sharded mat-vec): side streams that carry the copy-engine transfers + per-slice flag
+  // publications, and the exchange counter every rank advances in lockstep (see enqueue_matvec)
+  std::vector<cudaStream_t> xchg_streams;
+  std::vector<cudaEvent_t> xchg_done;   // one per side stream: its last transfer + publication
+  cudaEvent_t xchg_ready = nullptr;     // main stream: the column to exchange is final
+  unsigned long long x_seq = 0;
+  // kernels whose opt-in dynamic shared memory limit has been raised on THIS device (the attribute is per device
+  // and per function; a process may drive several GPUs through several contexts)
+  std::vector<const void *> smem_attr_done;
 };
 
 // Device memory comes from the device's stream-ordered pool (cudaMallocAsync) with an unlimited
@@ -188,15 +199,15 @@ static cudaEvent_t prof_event(b2a_ctx *c) {
   }
   return e;
 }
-static inline void prof_begin(b2a_ctx *c, int kind, double bytes, int gate_step = 0) {
+static inline void prof_begin(b2a_ctx *c, int kind, double bytes, int gate_step = 0, cudaStream_t st = nullptr) {
   if (!c->prof_on) return;
   b2a_ctx::ProfRec r{kind, bytes, gate_step, prof_event(c), prof_event(c), 0.0, 0};
-  cudaEventRecord(r.e0, c->stream);
+  cudaEventRecord(r.e0, st ? st : c->stream);
   c->prof_pending.push_back(r);
 }
-static inline void prof_end(b2a_ctx *c) {
+static inline void prof_end(b2a_ctx *c, cudaStream_t st = nullptr) {
   if (!c->prof_on) return;
-  cudaEventRecord(c->prof_pending.back().e1, c->stream);
+  cudaEventRecord(c->prof_pending.back().e1, st ? st : c->stream);
 }
 // call after a stream synchronisation; info[step - info_base] bit0 tells whether the gated
 // second pass of `step` really ran (gated-off launches are dropped from the statistics)
@@ -248,6 +259,10 @@ struct b2a_op {
   // column blocking (x larger than L2 and scattered columns): block-major CSR, d_ptr holds nblocks row-pointer
   // arrays of n_local+1 entries each (absolute positions in d_idx / d_vals)
   int nblocks = 1;
+  // row-sharded operators: the column blocks are the OWNER blocks of x (block b = columns of rank b), so that one
+  // launch per owner can start as soon as that rank's slice has arrived (staged exchange)
+  bool owner_blocks = false;
+  int64_t owner_W = 0;  // rows per rank of the uniform partition the blocks were cut for
   b2a_matvec_fn fn = nullptr;
   void *user = nullptr;
 };
@@ -297,6 +312,19 @@ struct b2a_ws {
   int sweep_pdl = 1;
   unsigned long long *sweep_trace = nullptr;  // per-CTA phase timestamps of the last fused launch (B2A_SWEEP_TRACE=1)
   int x_pushed_col = -1;  // 0-based column whose normalised content currently sits in every rank's x buffer
+  // staged exchange (default on row-sharded workspaces that own the peer block; B2A_XCHG=0 selects the push from
+  // inside the normalising kernel): copy-engine transfers on side streams, one flag per owner slice, the mat-vec
+  // runs owner block by owner block behind the arrivals.  xchg_sm = 1: SM copy kernels instead of copy engines.
+  bool xchg_staged = false;
+  int xchg_sm = 0;
+  unsigned int *xchg_ticket = nullptr;  // last-CTA counters of the SM copy kernels, one per side stream
+  // rotation: Q travels host -> device through two alternating pinned slots (no stream synchronisation per
+  // rotation: a slot is re-used only after the event behind its last copy)
+  size_t q_bytes = 0, qpin_off = 0;
+  cudaEvent_t qev[2] = {nullptr, nullptr};
+  bool q_used[2] = {false, false};
+  int q_slot = 0;
+  int rotate_mode = 1;  // 1 = TMA + DMMA kernel (kernels_rotate_mma.cuh), 0 = shared-memory DFMA kernels (B2A_ROTATE=0)
   int tune_rt_dots = 0, tune_rt_upd = 0, tune_stages = 0, tune_ctas = 1, tune_l2promo = 2;  // experiment overrides (env)
 };
 
@@ -315,7 +343,7 @@ namespace eng {
 static bool g_pdl = !(getenv("B2A_PDL") && getenv("B2A_PDL")[0] == '0');
 // Scoped override: the mat-vec that follows a fused sweep kernel is a plain stream-ordered launch (measured on
 // B200, tools/sweepbench.py: its CTAs scheduled early behind the persistent kernel cost ~10 us per step).
-static bool g_pdl_off = false;
+static thread_local bool g_pdl_off = false;
 struct PdlScope {
   bool saved;
   explicit PdlScope(bool off) : saved(g_pdl_off) { g_pdl_off = g_pdl_off || off; }
@@ -491,9 +519,14 @@ static bool tma_geometry(const b2a_ws *ws, int ncols, size_t elem, bool update, 
   return true;
 }
 
-template <class K> static int set_smem_attr(K kern, size_t smem) {
-  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBudget));
-  (void)smem;
+// Raise a kernel's dynamic shared-memory limit once per context (= per device: the attribute is per device and
+// function, and one process may own contexts on several GPUs).
+template <class K> static int ensure_smem_attr(b2a_ctx *ctx, K kern, size_t bytes) {
+  const void *key = reinterpret_cast<const void *>(kern);
+  for (const void *p : ctx->smem_attr_done)
+    if (p == key) return B2A_OK;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  ctx->smem_attr_done.push_back(key);
   return B2A_OK;
 }
 
@@ -501,11 +534,7 @@ template <class DT, int CPW>
 static int launch_dots_tma_inst(b2a_ws *ws, const DT *v, int ncols, const b2a::TmaGeom &g, size_t smem, int grid,
                                 DT *hout, double *nrm2, const double *g_rsq, const double *g_w1sq, int gate_step) {
   auto kern = b2a::cgs_dots_tma_kernel<DT, CPW>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    B2A_TRY(set_smem_attr(kern, smem));
-    attr_done = true;
-  }
+  B2A_TRY(ensure_smem_attr(ws->ctx, kern, kTmaSmemBudget));
   CUtensorMap tm;
   if (!make_panel_tmap(ws, ncols, g.RT, &tm)) return fail(B2A_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   (void)v;  // v is column `ncols` of the tensor map
@@ -543,11 +572,7 @@ static int launch_update_tma_inst(b2a_ws *ws, DT *v, int ncols, const b2a::TmaGe
                                   const DT *h, DT *cout, double *nrm2, const double *g_rsq, const double *g_w1sq,
                                   int gate_step) {
   auto kern = b2a::cgs_update_tma_kernel<DT, CPW, SPEC>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    B2A_TRY(set_smem_attr(kern, smem));
-    attr_done = true;
-  }
+  B2A_TRY(ensure_smem_attr(ws->ctx, kern, kTmaSmemBudget));
   CUtensorMap tm;
   if (!make_panel_tmap(ws, ncols, g.RT, &tm)) return fail(B2A_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   prof_begin(ws->ctx, B2A_K_UPDATE, (double)(ncols + 2) * ws->n_local * sizeof(DT), gate_step);
@@ -588,17 +613,14 @@ static bool fused_sweep_on(const b2a_ws *ws) {
   if (ws->ctx->world == 1) return ws->fused_sweep >= 1;
   // row-sharded: the kernel all-reduces inside its grid barriers, which needs the NVLink peer block (a workspace
   // that fell back to host-launched NCCL collectives keeps the four-kernel path)
-  return ws->fused_sweep >= 2 && ws->peer.P == ws->ctx->world;
+  // default (fused_sweep == 1): fused whenever the exchange is staged, i.e. the kernel has nothing to push
+  return (ws->fused_sweep >= 2 || (ws->fused_sweep == 1 && ws->xchg_staged)) && ws->peer.P == ws->ctx->world;
 }
 
 template <class DT, int CPW>
 static int launch_sweep_inst(b2a_ws *ws, int j, int step, const b2a::TmaGeom &g, size_t smem, int grid, int push) {
   auto kern = b2a::cgs_sweep_tma_kernel<DT, CPW>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBudget + 2048));
-    attr_done = true;
-  }
+  B2A_TRY(ensure_smem_attr(ws->ctx, kern, kTmaSmemBudget + 2048));
   PdlScope pdl_scope(!(ws->sweep_pdl & 1));
   CUtensorMap tm;
   if (!make_panel_tmap(ws, j, g.RT, &tm)) return fail(B2A_ERR_CUDA, "cuTensorMapEncodeTiled failed");
@@ -675,7 +697,7 @@ template <class DT> static int enqueue_cgs(b2a_ws *ws, int j, int mode, int step
   const bool fused = tma && ws->peer.P > 1;
   if (mode == 0 && j >= 1 && tma && fused_sweep_on(ws)) {
     // the whole orthogonalisation as one persistent kernel with in-kernel grid barriers
-    const int push = (ws->peer.P > 1 && ws->peer_x && !ws->push_separate) ? 1 : 0;
+    const int push = (ws->peer.P > 1 && ws->peer_x && !ws->push_separate && !ws->xchg_staged) ? 1 : 0;
     const int s = launch_sweep<DT>(ws, j, step, push);
     if (s == B2A_OK) {
       ws->x_pushed_col = push ? j : -1;
@@ -718,7 +740,7 @@ template <class DT> static int enqueue_cgs(b2a_ws *ws, int j, int mode, int step
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * ws->finish_grid_mult, cdiv(nvec, 256 * 4)));
   DT *Hcol = reinterpret_cast<DT *>(ws->dH) + (int64_t)(std::max(j, 1) - 1) * (ws->maxdim + 1);
   prof_begin(ctx, B2A_K_FINISH, 2.0 * ws->n_local * sizeof(DT));
-  const int push = (mode == 0 && ws->peer.P > 1 && ws->peer_x && !ws->push_separate) ? 1 : 0;  // Arnoldi step: the new column is the next mat-vec input
+  const int push = (mode == 0 && ws->peer.P > 1 && ws->peer_x && !ws->push_separate && !ws->xchg_staged) ? 1 : 0;  // Arnoldi step: the new column is the next mat-vec input
   CUDA_TRY(launch_pdl(b2a::cgs_finish_kernel<DT>, (unsigned)grid, 256u, 0, ctx->stream, v, ws->n_local, j,
                       (const DT *)h1, (const DT *)h2, (const double *)rsq, (const double *)w1sq,
                       (const double *)ws->w2sq, Hcol, ws->dinfo + j, ws->state, step, mode, ws->peer, ws->row_offset,
@@ -733,45 +755,77 @@ template <class DT> static int enqueue_cgs(b2a_ws *ws, int j, int mode, int step
 // ---- operator -------------------------------------------------------------------
 static double op_bytes(const b2a_op *A);
 
-struct XWait {
-  b2a::PeerView pv;
-  int wait = 0;
-};
-template <class DT, int LPR, int U>
-static void launch_spmv_vec_u(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms,
-                              const XWait &xw) {
+using b2a::XWait;
+
+// vector kernel, one launch: rowptr / accumulate select the column block, xw what the launch waits for
+template <class DT, int LPR, int U, bool HINT, bool COH>
+static cudaError_t launch_spmv_vec_one(b2a_op *A, const int64_t *rowptr, const DT *x, DT *y, const int *poison,
+                                       cudaStream_t st, int sms, const XWait &xw, int accumulate) {
   const int64_t threads = cdiv(A->n_local, U) * LPR;
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * A->grid_mult, cdiv(threads, 256)));
-  (void)launch_pdl(b2a::spmv_csr_vector_kernel<DT, LPR, U, false>, (unsigned)grid, 256u, 0, st, A->n_local,
-                   (const int64_t *)A->d_ptr, (const int32_t *)A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y,
-                   poison, xw.pv, xw.wait, 0);
+  return launch_pdl(b2a::spmv_csr_vector_kernel<DT, LPR, U, HINT, COH>, (unsigned)grid, 256u, 0, st, A->n_local, rowptr,
+                    (const int32_t *)A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y, poison, xw, accumulate);
 }
-// column-blocked operator: one pass per block, L2-hinted loads, the first pass writes y, the others accumulate
+template <class DT, int LPR, int U>
+static cudaError_t launch_spmv_vec_u(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms,
+                                     const XWait &xw) {
+  if (xw.mode) return launch_spmv_vec_one<DT, LPR, 2, false, true>(A, A->d_ptr, x, y, poison, st, sms, xw, 0);
+  return launch_spmv_vec_one<DT, LPR, U, false, false>(A, A->d_ptr, x, y, poison, st, sms, xw, 0);
+}
+// column-blocked operator (x larger than L2): one pass per block, L2-hinted loads, the first pass writes y, the
+// others accumulate; every pass gathers from the same x, so only the first one waits
 template <class DT, int LPR>
-static void launch_spmv_blocked(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms,
-                                const XWait &xw, int64_t *launches) {
-  constexpr int U = 2;
-  const int64_t threads = cdiv(A->n_local, U) * LPR;
-  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * A->grid_mult, cdiv(threads, 256)));
+static cudaError_t launch_spmv_blocked(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms,
+                                       const XWait &xw, int64_t *launches) {
   for (int b = 0; b < A->nblocks; ++b) {
-    (void)launch_pdl(b2a::spmv_csr_vector_kernel<DT, LPR, U, true>, (unsigned)grid, 256u, 0, st, A->n_local,
-                     (const int64_t *)(A->d_ptr + (size_t)b * (A->n_local + 1)), (const int32_t *)A->d_idx,
-                     reinterpret_cast<const DT *>(A->d_vals), x, y, poison, xw.pv, b == 0 ? xw.wait : 0, b > 0 ? 1 : 0);
+    const int64_t *rp = A->d_ptr + (size_t)b * (A->n_local + 1);
+    cudaError_t e;
+    if (xw.mode) {
+      XWait w = xw;
+      if (b > 0) w.mode = 0;
+      e = launch_spmv_vec_one<DT, LPR, 2, true, true>(A, rp, x, y, poison, st, sms, w, b > 0 ? 1 : 0);
+    } else {
+      e = launch_spmv_vec_one<DT, LPR, 2, true, false>(A, rp, x, y, poison, st, sms, xw, b > 0 ? 1 : 0);
+    }
+    if (e != cudaSuccess) return e;
     if (b > 0) ++*launches;
   }
+  return cudaSuccess;
+}
+// operator stored by OWNER block (row-sharded, staged exchange): pass 0 = this rank's own columns, gathered
+// straight from the workspace column (no wait, no copy); pass k = the columns of rank (rank + k) % P, gathered from
+// the exchange buffer once that rank's slice has arrived - the order in which the staged exchange delivers them
+template <class DT, int LPR>
+static cudaError_t launch_spmv_owner(b2a_op *A, const DT *x_local_shifted, const DT *x_buf, DT *y, const int *poison,
+                                     cudaStream_t st, int sms, const XWait &xw, int64_t *launches) {
+  const int P = xw.pv.P, me = xw.pv.rank;
+  for (int k = 0; k < P; ++k) {
+    const int owner = (me + k) % P;
+    const int64_t *rp = A->d_ptr + (size_t)owner * (A->n_local + 1);
+    cudaError_t e;
+    if (k == 0) {
+      XWait w;
+      e = launch_spmv_vec_one<DT, LPR, 2, false, false>(A, rp, x_local_shifted, y, poison, st, sms, w, 0);
+    } else {
+      XWait w = xw;
+      w.mode = 2;
+      w.owner = owner;
+      e = launch_spmv_vec_one<DT, LPR, 2, false, true>(A, rp, x_buf, y, poison, st, sms, w, 1);
+      ++*launches;
+    }
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 template <class DT, int LPR>
-static void launch_spmv_vec(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms,
-                            const XWait &xw) {
-  if (A->nblocks > 1) {
-    launch_spmv_blocked<DT, LPR>(A, x, y, poison, st, sms, xw, &A->ctx->launches);
-    return;
-  }
+static cudaError_t launch_spmv_vec(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms,
+                                   const XWait &xw) {
+  if (A->nblocks > 1) return launch_spmv_blocked<DT, LPR>(A, x, y, poison, st, sms, xw, &A->ctx->launches);
   switch (A->rows_in_flight) {
-    case 1: launch_spmv_vec_u<DT, LPR, 1>(A, x, y, poison, st, sms, xw); break;
-    case 4: launch_spmv_vec_u<DT, LPR, 4>(A, x, y, poison, st, sms, xw); break;
-    case 8: launch_spmv_vec_u<DT, LPR, 8>(A, x, y, poison, st, sms, xw); break;
-    default: launch_spmv_vec_u<DT, LPR, 2>(A, x, y, poison, st, sms, xw); break;
+    case 1: return launch_spmv_vec_u<DT, LPR, 1>(A, x, y, poison, st, sms, xw);
+    case 4: return launch_spmv_vec_u<DT, LPR, 4>(A, x, y, poison, st, sms, xw);
+    case 8: return launch_spmv_vec_u<DT, LPR, 8>(A, x, y, poison, st, sms, xw);
+    default: return launch_spmv_vec_u<DT, LPR, 2>(A, x, y, poison, st, sms, xw);
   }
 }
 
@@ -795,11 +849,7 @@ static int launch_spmv_tma_inst(b2a_op *A, const DT *x, DT *y, const int *poison
   if (A->tma_stages >= 2) stages = A->tma_stages;
   stages = std::max(2, std::min(stages, std::max(2, tpc)));
   const size_t smem = 128 + (size_t)stages * stage;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBudget));
-    attr_done = true;
-  }
+  B2A_TRY(ensure_smem_attr(ctx, kern, kTmaSmemBudget));
   kern<<<g2, b2a::kTmaThreads, smem, ctx->stream>>>(A->n_local, A->d_ptr, A->d_idx,
                                                       reinterpret_cast<const DT *>(A->d_vals), A->d_tile_row, A->ntiles,
                                                       tpc, stages, x, y, poison);
@@ -816,6 +866,76 @@ template <class DT> static int launch_spmv_tma(b2a_op *A, const DT *x, DT *y, co
   }
 }
 
+// ---- staged x exchange ------------------------------------------------------------------------------------
+// Row-sharded mat-vec input (SURVEY 8(e) "x-exchange"): rank s owns rows [off_s, off_s + cnt_s) of the new basis
+// vector and every rank needs (in general) all of it.  Stage k = 1 .. P-1 sends this rank's slice to rank
+// (rank - k) mod P - a permutation per stage, so every NVLink port carries one slice in and one out at a time -
+// as ONE copy-engine transfer (no SM store-issue limit, no SMs taken from the mat-vec) followed by a one-thread
+// kernel that publishes the exchange number in the receiver's flag for this sender (st.release.sys; stream order
+// puts it behind the copy).  The receiver runs its mat-vec owner block by owner block in the same order
+// (own block, rank+1, rank+2, ...): the gathers on the blocks that have arrived hide the transfer of the others.
+// Two x buffers (exchange-number parity): a rank that is one mat-vec ahead never overwrites what a peer still reads.
+static int xchg_ensure_streams(b2a_ctx *ctx, int want) {
+  while ((int)ctx->xchg_streams.size() < want) {
+    cudaStream_t s;
+    int lo = 0, hi = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CUDA_TRY(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi));  // transfers go first
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->xchg_streams.push_back(s);
+    ctx->xchg_done.push_back(e);
+  }
+  if (!ctx->xchg_ready) CUDA_TRY(cudaEventCreateWithFlags(&ctx->xchg_ready, cudaEventDisableTiming));
+  return B2A_OK;
+}
+
+static int g_xchg_nstreams = getenv("B2A_XCHG_STREAMS") ? std::max(1, atoi(getenv("B2A_XCHG_STREAMS"))) : 3;
+
+// Enqueue the exchange of workspace column jsrc0; returns the exchange number the consumers wait for.
+template <class DT> static int enqueue_xchg(b2a_ws *ws, const DT *xl, unsigned long long *seq_out) {
+  b2a_ctx *ctx = ws->ctx;
+  const b2a::PeerView &pv = ws->peer;
+  const int P = pv.P, me = pv.rank;
+  const int ns = std::min(g_xchg_nstreams, P - 1);
+  B2A_TRY(xchg_ensure_streams(ctx, ns));
+  const unsigned long long seq = ++ctx->x_seq;
+  const size_t bytes = (size_t)ws->n_local * sizeof(DT);
+  const size_t xoff = pv.off_x + (seq & 1ull) * pv.x_stride + (size_t)ws->row_offset * sizeof(DT);
+  CUDA_TRY(cudaEventRecord(ctx->xchg_ready, ctx->stream));
+  for (int i = 0; i < ns; ++i) CUDA_TRY(cudaStreamWaitEvent(ctx->xchg_streams[i], ctx->xchg_ready, 0));
+  // timed on the first side stream: with ns streams it carries ceil((P-1)/ns) of the P-1 stages
+  const int on_first = (P - 1 + ns - 1) / ns;
+  prof_begin(ctx, B2A_K_XCHG, (double)bytes * on_first, 0, ctx->xchg_streams[0]);
+  for (int k = 1; k < P; ++k) {
+    const int dst = (me - k + P) % P;
+    cudaStream_t st = ctx->xchg_streams[(k - 1) % ns];
+    unsigned long long *flag = reinterpret_cast<unsigned long long *>(pv.peer[dst] + pv.off_flag_xs) + me;
+    if (ws->xchg_sm) {
+      const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(ws->xchg_sm, cdiv((int64_t)bytes, 256 * 16 * 4)));
+      b2a::xsend_kernel<<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const double *>(xl),
+                                                        reinterpret_cast<double *>(pv.peer[dst] + xoff),
+                                                        (int64_t)(bytes / 8), flag, seq,
+                                                        ws->xchg_ticket + ((k - 1) % ns));
+    } else {
+      if (bytes) CUDA_TRY(cudaMemcpyAsync(pv.peer[dst] + xoff, xl, bytes, cudaMemcpyDeviceToDevice, st));
+      b2a::xflag_kernel<<<1, 32, 0, st>>>(flag, seq);
+    }
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  for (int i = 0; i < ns; ++i) CUDA_TRY(cudaEventRecord(ctx->xchg_done[i], ctx->xchg_streams[i]));
+  if (ctx->prof_on) {  // e1 of the exchange record: after the last operation of the first side stream
+    for (auto it = ctx->prof_pending.rbegin(); it != ctx->prof_pending.rend(); ++it)
+      if (it->kind == B2A_K_XCHG) {
+        cudaEventRecord(it->e1, ctx->xchg_streams[0]);
+        break;
+      }
+  }
+  *seq_out = seq;
+  return B2A_OK;
+}
+
 // y = A x for the local rows; x_local / y are workspace columns.
 template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, int jdst0) {
   b2a_ctx *ctx = ws->ctx;
@@ -829,7 +949,25 @@ template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, 
   }
   const DT *x = xl;
   XWait xw;
-  if (ctx->world > 1 && ws->peer.P > 1 && ws->peer_x) {
+  bool owner_passes = false;
+  int xchg_streams_used = 0;
+  if (ctx->world > 1 && ws->peer.P > 1 && ws->xchg_staged) {
+    unsigned long long seq = 0;
+    B2A_TRY(enqueue_xchg<DT>(ws, xl, &seq));
+    xchg_streams_used = std::min(g_xchg_nstreams, ws->peer.P - 1);
+    const DT *xbuf = reinterpret_cast<const DT *>(ws->peer.peer[ws->peer.rank] + ws->peer.off_x + (seq & 1ull) * ws->peer.x_stride);
+    xw.pv = ws->peer;
+    xw.want = seq;
+    x = xbuf;
+    if (A->owner_blocks && A->kind == OP_CSR) {
+      owner_passes = true;
+    } else {
+      // operator not stored by owner block: own slice into the buffer (stream-ordered), then wait for all the others
+      CUDA_TRY(cudaMemcpyAsync(const_cast<DT *>(xbuf) + ws->row_offset, xl, (size_t)ws->n_local * sizeof(DT),
+                               cudaMemcpyDeviceToDevice, ctx->stream));
+      xw.mode = 3;
+    }
+  } else if (ctx->world > 1 && ws->peer.P > 1 && ws->peer_x) {
     // push model over NVLink peer memory: normally the normalising cgs_finish kernel of the previous step
     // has already pushed this column into every rank's x buffer; otherwise push it explicitly
     if (ws->x_pushed_col != jsrc0) {
@@ -842,7 +980,7 @@ template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, 
       ws->x_pushed_col = jsrc0;
     }
     xw.pv = ws->peer;
-    xw.wait = 1;
+    xw.mode = 1;
     x = reinterpret_cast<const DT *>(ws->peer.peer[ws->peer.rank] + ws->peer.off_x);
   } else if (ctx->world > 1) {
     // x-exchange: every shard needs (in general) all of x.  Uniform partitions use one
@@ -862,6 +1000,7 @@ template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, 
   }
   PdlScope pdl_scope(fused_sweep_on(ws) && !(ws->sweep_pdl & 2));
   prof_begin(ctx, B2A_K_SPMV, op_bytes(A));
+  cudaError_t le = cudaSuccess;
   if (A->kind == OP_CSC_SCATTER) {
     b2a::zero_vector_kernel<DT><<<(unsigned)std::min<int64_t>(ctx->num_sms * 8, std::max<int64_t>(1, cdiv(A->n_local, 256))), 256, 0, ctx->stream>>>(y, A->n_local, poison);
     ctx->launches++;
@@ -873,6 +1012,16 @@ template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, 
       case 16: launch_spmv_csc<DT, 16>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
       default: launch_spmv_csc<DT, 32>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
     }
+  } else if (owner_passes) {
+    const DT *xls = xl - ws->row_offset;  // global column c of the own block -> workspace row c - row_offset
+    switch (A->lpr) {
+      case 1:
+      case 2: le = launch_spmv_owner<DT, 2>(A, xls, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches); break;
+      case 4: le = launch_spmv_owner<DT, 4>(A, xls, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches); break;
+      case 8: le = launch_spmv_owner<DT, 8>(A, xls, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches); break;
+      case 16: le = launch_spmv_owner<DT, 16>(A, xls, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches); break;
+      default: le = launch_spmv_owner<DT, 32>(A, xls, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches); break;
+    }
   } else if (A->use_tma && ctx->world == 1 && A->nblocks == 1) {
     B2A_TRY(launch_spmv_tma<DT>(A, x, y, poison, ctx));
   } else {
@@ -880,25 +1029,34 @@ template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, 
       case 1: {
         const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, cdiv(A->n_local, 256)));
         if (A->nblocks > 1) {
-          launch_spmv_blocked<DT, 2>(A, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches);
+          le = launch_spmv_blocked<DT, 2>(A, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches);
           break;
         }
-        b2a::spmv_csr_scalar_kernel<DT><<<(unsigned)grid, 256, 0, ctx->stream>>>(
-            A->n_local, A->d_ptr, A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y, poison, xw.pv, xw.wait);
+        if (xw.mode)
+          b2a::spmv_csr_scalar_kernel<DT, true><<<(unsigned)grid, 256, 0, ctx->stream>>>(
+              A->n_local, A->d_ptr, A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y, poison, xw, 0);
+        else
+          b2a::spmv_csr_scalar_kernel<DT, false><<<(unsigned)grid, 256, 0, ctx->stream>>>(
+              A->n_local, A->d_ptr, A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y, poison, xw, 0);
         break;
       }
-      case 2: launch_spmv_vec<DT, 2>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
-      case 4: launch_spmv_vec<DT, 4>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
-      case 8: launch_spmv_vec<DT, 8>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
-      case 16: launch_spmv_vec<DT, 16>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
-      default: launch_spmv_vec<DT, 32>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
+      case 2: le = launch_spmv_vec<DT, 2>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
+      case 4: le = launch_spmv_vec<DT, 4>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
+      case 8: le = launch_spmv_vec<DT, 8>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
+      case 16: le = launch_spmv_vec<DT, 16>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
+      default: le = launch_spmv_vec<DT, 32>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
     }
   }
   prof_end(ctx);
   ctx->launches++;
+  CUDA_TRY(le);
   CUDA_TRY(cudaGetLastError());
+  // whatever follows on the main stream may overwrite the column that is still being sent: order it behind the
+  // outgoing transfers (they finish while the gathers above wait for the incoming ones)
+  for (int i = 0; i < xchg_streams_used; ++i) CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ctx->xchg_done[i], 0));
   return B2A_OK;
 }
+
 
 // ---- basis rotation ---------------------------------------------------------------
 template <class DT, int R>
@@ -960,23 +1118,183 @@ template <class DT> static bool try_rotate2(b2a_ws *ws, int col0, int K, int N, 
   }
 }
 
-// V[:, col0 : col0+N) <- V[:, col0 : col0+K) * Qp  (Qp = K x N packed, host), optional column move
+// ---- TMA + DMMA rotation (kernels_rotate_mma.cuh) ------------------------------------------------------------
+struct RotPlan {
+  b2a::RotGeom g;
+  int NT = 4, NCH = 1, KS = 1, b_in_smem = 1, grid = 1;
+  size_t smem = 0, b_elems = 0;
+};
+// Largest row tile (16 rows per consumer warp) that leaves at least two ring stages, Q fragments in shared memory
+// when they fit beside them.
+static bool rot_plan(const b2a_ws *ws, int K, int N, bool cplx, RotPlan *p) {
+  const int inner = cplx ? 2 : 1, parts = cplx ? 2 : 1;
+  const int ntiles_n = (N * inner + 7) / 8;  // 8-wide output tiles of the real view
+  int best_nt = 4, best_pad = 1 << 30;
+  for (int nt = 4; nt >= 1; --nt) {
+    const int pad = (int)cdiv(ntiles_n, nt) * nt;
+    if (pad < best_pad) {
+      best_pad = pad;
+      best_nt = nt;
+    }
+  }
+  p->NT = best_nt;
+  p->NCH = (int)cdiv(ntiles_n, best_nt);
+  p->KS = (K + 3) / 4;
+  p->b_elems = (size_t)p->KS * p->NCH * p->NT * parts * 32;
+  const int nbox = (int)cdiv(K, 256);
+  const int box_cols = (int)round_up(cdiv(K, nbox), 4);
+  const int kpad = nbox * box_cols;
+  const size_t b_bytes = (p->b_elems * 8 + 127) / 128 * 128;
+  const size_t budget = kTmaSmemBudget - 256;
+  const int order[8][2] = {{1, 8}, {1, 4}, {0, 8}, {0, 4}, {1, 2}, {0, 2}, {1, 1}, {0, 1}};
+  for (const auto &o : order) {
+    const int bsm = o[0], warps = o[1], R = 16 * warps;
+    if ((int64_t)R / 2 >= std::max<int64_t>(ws->n_local, 1) && warps > 1) continue;  // tiny vectors: smaller tiles
+    const size_t stage = (size_t)kpad * R * inner * 8;
+    const size_t avail = budget - (bsm ? std::min(b_bytes, budget) : 0);
+    int stages = (int)std::min<size_t>(b2a::kTmaMaxStages, avail / stage);
+    if (bsm && b_bytes >= budget) continue;
+    if (stages < 2) continue;
+    const int64_t ntiles = cdiv(std::max<int64_t>(ws->n_local, 1), R);
+    if (ntiles > 2000000000LL) return false;
+    int gr = (int)std::min<int64_t>(ws->ctx->num_sms, ntiles);
+    const int tpc = (int)cdiv(ntiles, gr);
+    gr = (int)cdiv(ntiles, tpc);
+    stages = std::min(stages, std::max(2, tpc));
+    p->g.R = R;
+    p->g.warps = warps;
+    p->g.stages = stages;
+    p->g.tiles_per_cta = tpc;
+    p->g.ntiles = (int)ntiles;
+    p->g.nbox = nbox;
+    p->g.box_cols = box_cols;
+    p->g.kpad = kpad;
+    p->b_in_smem = bsm;
+    p->grid = gr;
+    p->smem = 256 + (bsm ? b_bytes : 0) + (size_t)stages * stage;
+    return true;
+  }
+  return false;
+}
+
+// Tensor map over the K input columns [col0, col0 + K) of V, box = R rows x box_cols columns.
+static bool make_rot_tmap(const b2a_ws *ws, int col0, int K, const b2a::RotGeom &g, CUtensorMap *tm) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  const cuuint64_t inner = ws->esz / 8;
+  cuuint64_t gdim[2] = {(cuuint64_t)ws->ld * inner, (cuuint64_t)K};
+  cuuint64_t gstride[1] = {(cuuint64_t)ws->ld * ws->esz};
+  cuuint32_t box[2] = {(cuuint32_t)(g.R * inner), (cuuint32_t)g.box_cols};
+  cuuint32_t estr[2] = {1, 1};
+  void *base = reinterpret_cast<char *>(ws->dV) + (size_t)col0 * ws->ld * ws->esz;
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) ==
+         CUDA_SUCCESS;
+}
+
+// Q (K x N packed, column-major) in MMA B-fragment order, see kernels_rotate_mma.cuh
+template <class HT> static void pack_b_fragments(const HT *Qp, int K, int N, const RotPlan &p, double *out);
+template <> void pack_b_fragments<double>(const double *Qp, int K, int N, const RotPlan &p, double *out) {
+  const int NTT = p.NCH * p.NT;
+  for (int ks = 0; ks < p.KS; ++ks)
+    for (int nt = 0; nt < NTT; ++nt)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int k = 4 * ks + (lane & 3), n = 8 * nt + (lane >> 2);
+        out[((size_t)ks * NTT + nt) * 32 + lane] = (k < K && n < N) ? Qp[(size_t)n * K + k] : 0.0;
+      }
+}
+template <> void pack_b_fragments<cplx>(const cplx *Qp, int K, int N, const RotPlan &p, double *out) {
+  const int NTT = p.NCH * p.NT;
+  for (int ks = 0; ks < p.KS; ++ks)
+    for (int nt = 0; nt < NTT; ++nt)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int c = 4 * ks + (lane & 3), np = 8 * nt + (lane >> 2);
+        const int o = np >> 1, comp = np & 1;
+        const cplx q = (c < K && o < N) ? Qp[(size_t)o * K + c] : cplx(0.0, 0.0);
+        double *dst = out + ((size_t)ks * NTT + nt) * 64 + lane;
+        dst[0] = comp == 0 ? q.real() : q.imag();    // multiplies Re V
+        dst[32] = comp == 0 ? -q.imag() : q.real();  // multiplies Im V
+      }
+}
+
+template <bool CPLX, int NT>
+static int launch_rotate_mma_inst(b2a_ws *ws, const CUtensorMap &tm, int col0, int N, const RotPlan &p, int move_src,
+                                  int move_dst) {
+  auto kern = b2a::rotate_mma_kernel<CPLX, NT>;
+  B2A_TRY(ensure_smem_attr(ws->ctx, kern, kTmaSmemBudget));
+  kern<<<(unsigned)p.grid, b2a::kRotThreads, p.smem, ws->ctx->stream>>>(
+      tm, reinterpret_cast<double *>(ws->dV), ws->ld, col0, N, reinterpret_cast<const double *>(ws->dQ), p.KS, p.NCH,
+      p.g, move_src, move_dst, p.b_in_smem);
+  CUDA_TRY(cudaGetLastError());
+  return B2A_OK;
+}
+
+// host -> device copy of a small array through one of the two pinned Q slots, no stream synchronisation
+static int stage_q(b2a_ws *ws, size_t bytes, double **host_slot) {
+  if (bytes > ws->q_bytes) return fail(B2A_ERR_INTERNAL, "rotation: Q staging slot too small");
+  const int slot = ws->q_slot ^= 1;
+  if (ws->q_used[slot]) CUDA_TRY(cudaEventSynchronize(ws->qev[slot]));
+  *host_slot = reinterpret_cast<double *>(ws->pinned + ws->qpin_off + (size_t)slot * ws->q_bytes);
+  return B2A_OK;
+}
+static int stage_q_send(b2a_ws *ws, const double *host_slot, size_t bytes) {
+  CUDA_TRY(cudaMemcpyAsync(ws->dQ, host_slot, bytes, cudaMemcpyHostToDevice, ws->ctx->stream));
+  CUDA_TRY(cudaEventRecord(ws->qev[ws->q_slot], ws->ctx->stream));
+  ws->q_used[ws->q_slot] = true;
+  return B2A_OK;
+}
+
+// returns 1 when this path cannot take the shape (caller falls back to the shared-memory DFMA kernels)
+template <class HT>
+static int rotate_mma(b2a_ws *ws, int col0, int K, int N, const HT *Qp, int move_src, int move_dst) {
+  using DT = typename Dev<HT>::type;
+  constexpr bool CPLX = b2a::Scalar<DT>::is_complex;
+  if (!ws->rotate_mode || !ws->use_tma || get_encode_tiled() == nullptr) return 1;
+  RotPlan p;
+  if (!rot_plan(ws, K, N, CPLX, &p)) return 1;
+  CUtensorMap tm;
+  if (!make_rot_tmap(ws, col0, K, p.g, &tm)) return 1;
+  double *slot = nullptr;
+  B2A_TRY(stage_q(ws, p.b_elems * 8, &slot));
+  pack_b_fragments<HT>(Qp, K, N, p, slot);
+  B2A_TRY(stage_q_send(ws, slot, p.b_elems * 8));
+  prof_begin(ws->ctx, B2A_K_ROTATE, (double)ws->n_local * sizeof(DT) * (K + N + (move_dst >= 0 ? 2.0 : 0.0)));
+  int s;
+  switch (p.NT) {
+    case 1: s = launch_rotate_mma_inst<CPLX, 1>(ws, tm, col0, N, p, move_src, move_dst); break;
+    case 2: s = launch_rotate_mma_inst<CPLX, 2>(ws, tm, col0, N, p, move_src, move_dst); break;
+    case 3: s = launch_rotate_mma_inst<CPLX, 3>(ws, tm, col0, N, p, move_src, move_dst); break;
+    default: s = launch_rotate_mma_inst<CPLX, 4>(ws, tm, col0, N, p, move_src, move_dst); break;
+  }
+  prof_end(ws->ctx);
+  ws->ctx->launches++;
+  return s;
+}
+
+// V[:, col0 : col0+N) <- V[:, col0 : col0+K) * Qp  (Qp = K x N packed, host), optional column move.
+// Asynchronous: the kernel is enqueued, Qp may be freed on return (it has been copied into a pinned slot).
 template <class HT>
 static int rotate(b2a_ws *ws, int col0, int K, int N, const HT *Qp, int move_src, int move_dst) {
   using DT = typename Dev<HT>::type;
   if (N <= 0 || K <= 0) return B2A_OK;
   ws->x_pushed_col = -1;
   if (move_src == move_dst) move_src = move_dst = -1;
-  CUDA_TRY(cudaMemcpyAsync(ws->dQ, Qp, (size_t)K * N * sizeof(HT), cudaMemcpyHostToDevice, ws->ctx->stream));
+  {
+    const int s = rotate_mma<HT>(ws, col0, K, N, Qp, move_src, move_dst);
+    if (s != 1) return s;
+  }
+  // fallback: Q as it is (K x N) through a pinned slot, shared-memory DFMA kernels
+  double *slot = nullptr;
+  const size_t qb = (size_t)K * N * sizeof(HT);
+  B2A_TRY(stage_q(ws, qb, &slot));
+  std::memcpy(slot, Qp, qb);
+  B2A_TRY(stage_q_send(ws, slot, qb));
   bool ok = try_rotate2<DT>(ws, col0, K, N, move_src, move_dst);
   if (!ok) ok = try_rotate<DT, 128>(ws, col0, K, N, move_src, move_dst);
   if (!ok) ok = try_rotate<DT, 64>(ws, col0, K, N, move_src, move_dst);
   if (!ok) ok = try_rotate<DT, 32>(ws, col0, K, N, move_src, move_dst);
   if (!ok) return fail(B2A_ERR_ARGUMENT, "basis rotation: Krylov dimension too large for one shared-memory tile");
   CUDA_TRY(cudaGetLastError());
-  // Qp is a host temporary of the caller: make sure the copy has been consumed
-  CUDA_TRY(cudaStreamSynchronize(ws->ctx->stream));
-  prof_collect(ws->ctx, nullptr, 0, 0);
   return B2A_OK;
 }
 
@@ -1182,6 +1500,8 @@ static int partialschur(b2a_ws *ws, b2a_op *A, int mindim, int maxdim, int nev, 
   double t1 = now_ms();
   hist->ms_small += t1 - t0;
   B2A_TRY((rotate_final<HT>(ws, nconverged, Q.p, Q.ld, st)));  // run.jl:382-383
+  CUDA_TRY(cudaStreamSynchronize(ws->ctx->stream));  // rotations are asynchronous; the call is synchronous on return
+  prof_collect(ws->ctx, nullptr, 0, 0);
   hist->ms_rotate += now_ms() - t1;
 
   if (eig_out) {
@@ -1292,6 +1612,9 @@ int b2a_ctx_destroy(b2a_ctx *ctx) {
   }
   for (auto e : ctx->prof_pool) cudaEventDestroy(e);
   peer_release(ctx);
+  for (auto st : ctx->xchg_streams) cudaStreamDestroy(st);
+  for (auto e : ctx->xchg_done) cudaEventDestroy(e);
+  if (ctx->xchg_ready) cudaEventDestroy(ctx->xchg_ready);
   if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
   if (ctx->d_zero) cudaFree(ctx->d_zero);
   for (auto &pc : ctx->pinned_cache) cudaFreeHost(pc.second);
@@ -1558,6 +1881,93 @@ static void build_col_blocks(RP rp, CI ci, const char *vals, size_t es, int64_t 
 }
 }  // extern "C++"
 
+// ---- structure validation (device pass over the uploaded arrays) -------------------------------------------
+// SparseMatrixCSC's constructor rejects malformed structure; here a 1-based array passed with idx_base = 0, a
+// decreasing pointer array or a column >= n would otherwise become out-of-bounds gathers (or red.add scatters).
+static int validate_structure(b2a_ctx *ctx, const int64_t *d_ptr, int64_t n_ptr, int64_t nnz, const int32_t *d_idx,
+                              int64_t idx_bound, const char *what) {
+  int *d_err = nullptr;
+  CUDA_TRY(dev_alloc(ctx, reinterpret_cast<void **>(&d_err), sizeof(int)));
+  cudaError_t e = cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream);
+  int err = 0;
+  if (e == cudaSuccess) {
+    const int64_t work = std::max<int64_t>(n_ptr, nnz);
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, cdiv(work, 256)));
+    b2a::validate_csr_kernel<<<grid, 256, 0, ctx->stream>>>(n_ptr, d_ptr, nnz, d_idx, idx_bound, d_err);
+    ctx->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  dev_free(ctx, d_err);
+  CUDA_TRY(e);
+  if (err & 1) return fail(B2A_ERR_ARGUMENT, std::string(what) + ": pointer array must start at 0, be non-decreasing and end at nnz");
+  if (err & 2) return fail(B2A_ERR_ARGUMENT, std::string(what) + ": index out of range (check idx_base)");
+  return B2A_OK;
+}
+
+// ---- owner blocks (row-sharded operators) --------------------------------------------------------------------
+// Reorder the uploaded shard block-major by owner rank of the column, on the device (kernels_blocks.cuh).  W = rows
+// per rank of the uniform partition, deduced from this rank's own block; if the block does not look like a uniform
+// partition the operator stays as it is (the mat-vec then waits for the whole exchange before its single pass).
+static int build_owner_blocks(b2a_ctx *ctx, b2a_op *op) {
+  const int P = ctx->world;
+  if (P < 2 || P > b2a::kMaxOwnerBlocks || op->n_local <= 0 || op->nnz <= 0) return B2A_OK;
+  if (getenv("B2A_OWNER_BLOCKS") && getenv("B2A_OWNER_BLOCKS")[0] == '0') return B2A_OK;
+  const int64_t W = cdiv(op->n_global, P);
+  if (op->row_offset != (int64_t)ctx->rank * W) return B2A_OK;
+  if (op->n_local != std::min<int64_t>(W, op->n_global - op->row_offset)) return B2A_OK;
+  const int64_t n = op->n_local, ld = n + 1, L = (int64_t)P * ld;
+  const size_t es = dtype_size(op->dtype);
+  int64_t *bptr = nullptr, *sums = nullptr;
+  int32_t *bcol = nullptr;
+  void *bval = nullptr;
+  const int64_t nchunks = cdiv(L, b2a::kScanChunk);
+  cudaError_t e = dev_alloc(ctx, reinterpret_cast<void **>(&bptr), (size_t)L * 8 + 64);
+  if (e == cudaSuccess) e = dev_alloc(ctx, reinterpret_cast<void **>(&sums), (size_t)nchunks * 8);
+  if (e == cudaSuccess) e = dev_alloc(ctx, reinterpret_cast<void **>(&bcol), (size_t)op->nnz * 4 + 64);
+  if (e == cudaSuccess) e = dev_alloc(ctx, &bval, (size_t)op->nnz * es + 64);
+  if (e == cudaSuccess) e = cudaMemsetAsync(bptr, 0, (size_t)L * 8, ctx->stream);
+  if (e == cudaSuccess) {
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 16, cdiv(n, 256)));
+    b2a::blk_count_kernel<<<grid, 256, 0, ctx->stream>>>(n, op->d_ptr, op->d_idx, W, bptr);
+    b2a::scan_partial_kernel<<<(unsigned)nchunks, b2a::kScanThreads, 0, ctx->stream>>>(bptr, L, sums);
+    b2a::scan_sums_kernel<<<1, b2a::kScanThreads, 0, ctx->stream>>>(sums, nchunks);
+    b2a::scan_apply_kernel<<<(unsigned)nchunks, b2a::kScanThreads, 0, ctx->stream>>>(bptr, L, sums);
+    if (op->dtype == B2A_F64)
+      b2a::blk_scatter_kernel<double><<<grid, 256, 0, ctx->stream>>>(n, op->d_ptr, op->d_idx,
+                                                                     reinterpret_cast<const double *>(op->d_vals), W, P,
+                                                                     bptr, bcol, reinterpret_cast<double *>(bval));
+    else
+      b2a::blk_scatter_kernel<cdouble><<<grid, 256, 0, ctx->stream>>>(n, op->d_ptr, op->d_idx,
+                                                                      reinterpret_cast<const cdouble *>(op->d_vals), W, P,
+                                                                      bptr, bcol, reinterpret_cast<cdouble *>(bval));
+    ctx->launches += 5;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  dev_free(ctx, sums);
+  if (e != cudaSuccess) {
+    dev_free(ctx, bptr);
+    dev_free(ctx, bcol);
+    dev_free(ctx, bval);
+    CUDA_TRY(e);
+  }
+  dev_free(ctx, op->d_ptr);
+  dev_free(ctx, op->d_idx);
+  dev_free(ctx, op->d_vals);
+  op->d_ptr = bptr;
+  op->d_idx = bcol;
+  op->d_vals = bval;
+  op->nblocks = P;
+  op->owner_blocks = true;
+  op->owner_W = W;
+  op->lpr = pick_lanes(op->nnz, n * P);
+  if (const char *env = getenv("B2A_SPMV_LPR")) op->lpr = atoi(env);
+  op->use_tma = false;
+  return B2A_OK;
+}
+
 int b2a_csr_create(b2a_ctx *ctx, int dtype, int64_t n_rows_local, int64_t n_global, int64_t row_offset, int64_t nnz,
                    const void *rowptr, const void *colind, const void *vals, int idx_width, int idx_base,
                    b2a_op **out) {
@@ -1580,9 +1990,23 @@ int b2a_csr_create(b2a_ctx *ctx, int dtype, int64_t n_rows_local, int64_t n_glob
     auto ci32 = [&](int64_t i) { return (int64_t) reinterpret_cast<const int32_t *>(colind)[i] - idx_base; };
     auto ci64 = [&](int64_t i) { return reinterpret_cast<const int64_t *>(colind)[i] - idx_base; };
     const size_t es = dtype_size(dtype);
-    op->nblocks = idx_width == 32 ? decide_col_blocks(rp32, ci32, n_rows_local, n_global, row_offset, es)
-                                  : decide_col_blocks(rp64, ci64, n_rows_local, n_global, row_offset, es);
+    // row-sharded operators are cut by OWNER block on the device instead (build_owner_blocks)
+    if (ctx->world == 1)
+      op->nblocks = idx_width == 32 ? decide_col_blocks(rp32, ci32, n_rows_local, n_global, row_offset, es)
+                                    : decide_col_blocks(rp64, ci64, n_rows_local, n_global, row_offset, es);
     if (op->nblocks > 1) {
+      // the host reordering indexes by column: check the structure first (the device check comes too late here)
+      bool sane = (idx_width == 32 ? rp32(0) : rp64(0)) == 0 && (idx_width == 32 ? rp32(n_rows_local) : rp64(n_rows_local)) == nnz;
+      for (int64_t r = 0; sane && r < n_rows_local; ++r)
+        sane = idx_width == 32 ? rp32(r) <= rp32(r + 1) : rp64(r) <= rp64(r + 1);
+      for (int64_t i = 0; sane && i < nnz; ++i) {
+        const int64_t c = idx_width == 32 ? ci32(i) : ci64(i);
+        sane = c >= 0 && c < n_global;
+      }
+      if (!sane) {
+        delete op;
+        return fail(B2A_ERR_ARGUMENT, "CSR: malformed structure (pointer array / index range; check idx_base)");
+      }
       std::vector<int64_t> bptr;
       std::vector<int32_t> bcol;
       std::vector<char> bval;
@@ -1601,6 +2025,7 @@ int b2a_csr_create(b2a_ctx *ctx, int dtype, int64_t n_rows_local, int64_t n_glob
         if (e != cudaSuccess) sb = fail(B2A_ERR_CUDA, cudaGetErrorString(e));
       }
       if (sb == B2A_OK) sb = cudaStreamSynchronize(ctx->stream) == cudaSuccess ? B2A_OK : fail(B2A_ERR_CUDA, "sync");
+      if (sb == B2A_OK) sb = validate_structure(ctx, op->d_ptr, (int64_t)bptr.size() - 1, nnz, op->d_idx, n_global, "CSR");
       if (sb != B2A_OK) {
         b2a_op_destroy(op);
         return sb;
@@ -1617,7 +2042,9 @@ int b2a_csr_create(b2a_ctx *ctx, int dtype, int64_t n_rows_local, int64_t n_glob
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) s = fail(B2A_ERR_CUDA, cudaGetErrorString(e));
   }
-  if (s == B2A_OK && n_rows_local > 0) {
+  if (s == B2A_OK) s = validate_structure(ctx, op->d_ptr, n_rows_local, nnz, op->d_idx, n_global, "CSR");
+  if (s == B2A_OK) s = build_owner_blocks(ctx, op);
+  if (s == B2A_OK && n_rows_local > 0 && !op->owner_blocks) {
     std::vector<int32_t> tiles;
     bool ok;
     const int max_nnz = dtype == B2A_C64 ? b2a::SpmvTile<cdouble>::max_nnz : b2a::SpmvTile<double>::max_nnz;
@@ -1654,6 +2081,13 @@ int b2a_csr_create_device(b2a_ctx *ctx, int dtype, int64_t n_rows_local, int64_t
   op->d_vals = const_cast<void *>(d_vals);
   op->owns = false;
   op_tuning(op);
+  {
+    const int sv = validate_structure(ctx, d_rowptr, n_rows_local, nnz, d_colind, n_global, "CSR");
+    if (sv != B2A_OK) {
+      delete op;
+      return sv;
+    }
+  }
   if (n_rows_local > 0) {
     // NOTE: the TMA-stream kernel reads 16-byte aligned supersets of the colind / vals slices, i.e. up
     // to 3 entries past nnz: borrowed arrays must be padded accordingly, else set B2A_SPMV_TMA=0.
@@ -1707,6 +2141,7 @@ int b2a_csc_create(b2a_ctx *ctx, int dtype, int64_t n_global, int64_t nnz, const
       if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
       if (e != cudaSuccess) s = fail(B2A_ERR_CUDA, cudaGetErrorString(e));
     }
+    if (s == B2A_OK) s = validate_structure(ctx, op->d_ptr, n_global, nnz, op->d_idx, n_global, "CSC");
     if (s != B2A_OK) {
       b2a_op_destroy(op);
       return s;
@@ -1723,6 +2158,10 @@ int b2a_csc_create(b2a_ctx *ctx, int dtype, int64_t n_global, int64_t nnz, const
   auto cptr = [&](int64_t c) {
     return idx_width == 32 ? host_idx<int32_t>(colptr, c, idx_base) : host_idx<int64_t>(colptr, c, idx_base);
   };
+  if (cptr(0) != 0 || cptr(n_global) != nnz)
+    return fail(B2A_ERR_ARGUMENT, "CSC: pointer array must start at 0 and end at nnz (check idx_base)");
+  for (int64_t c = 0; c < n_global; ++c)
+    if (cptr(c) > cptr(c + 1)) return fail(B2A_ERR_ARGUMENT, "CSC: pointer array must be non-decreasing");
   for (int64_t i = 0; i < nnz; ++i) {
     const int64_t r = ridx(i);
     if (r < 0 || r >= n_global) return fail(B2A_ERR_ARGUMENT, "row index out of range in CSC input");
@@ -1773,6 +2212,8 @@ int b2a_ws_destroy(b2a_ws *ws) {
   if (!ws) return B2A_OK;
   cudaSetDevice(ws->ctx->device);
   peer_teardown(ws);
+  for (int i = 0; i < 2; ++i)
+    if (ws->qev[i]) cudaEventDestroy(ws->qev[i]);
   dev_free(ws->ctx, ws->dV);
   dev_free(ws->ctx, ws->arena);
   dev_free(ws->ctx, ws->xfull);
@@ -1816,7 +2257,7 @@ static int peer_setup(b2a_ctx *ctx, b2a_ws *ws) {
   if (ctx->peer_busy) return B2A_OK;  // one workspace at a time owns the block; others use NCCL
   const int P = ctx->world;
   const int slot = (ws->maxdim + 2) * 2 + 2;  // doubles: [h (complex worst case) | norm]
-  const size_t x_bytes = (size_t)ws->n_global * ws->esz + 64;
+  const size_t x_bytes = ((size_t)ws->n_global * ws->esz + 64 + 255) / 256 * 256;
   if (ctx->peer_view.P == P && ctx->peer_slot >= slot && ctx->peer_x_bytes >= x_bytes) {
     ws->peer = ctx->peer_view;
     ws->peer_borrowed = true;
@@ -1833,8 +2274,9 @@ static int peer_setup(b2a_ctx *ctx, b2a_ws *ws) {
   const size_t o_hdr = carve(256);
   const size_t o_flag_ar = carve(sizeof(unsigned long long) * b2a::kPeerBufs * P);
   const size_t o_flag_x = carve(sizeof(unsigned long long) * P);
+  const size_t o_flag_xs = carve(sizeof(unsigned long long) * P);
   const size_t o_data = carve(sizeof(double) * b2a::kPeerBufs * P * slot);
-  const size_t o_x = carve(x_bytes);
+  const size_t o_x = carve(2 * x_bytes);  // two buffers: exchange-number parity (staged exchange)
   const size_t total = off;
   int okflag = 1;
   cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ctx->peer_local), total);
@@ -1910,7 +2352,9 @@ static int peer_setup(b2a_ctx *ctx, b2a_ws *ws) {
   pv.off_flag_ar = o_flag_ar;
   pv.off_data_ar = o_data;
   pv.off_flag_x = o_flag_x;
+  pv.off_flag_xs = o_flag_xs;
   pv.off_x = o_x;
+  pv.x_stride = x_bytes;
   pv.seq_ar = reinterpret_cast<unsigned long long *>(ctx->peer_local + o_hdr);
   pv.seq_x = pv.seq_ar + 1;
   pv.err = reinterpret_cast<int *>(pv.seq_ar + 2);
@@ -2003,11 +2447,20 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
   const size_t o_hb1 = carve((size_t)(m1 + 1) * es + 16);
   const size_t o_hb2 = carve((size_t)(m1 + 1) * es + 16);
   const size_t o_w2 = carve(16);
-  const size_t o_part = carve((size_t)66 * ws->dots_grid_max * es);
+  // per-CTA partial sums: four-kernel chain 66 x grid; fused sweep: one region per in-kernel grid barrier
+  const size_t o_part = carve(std::max<size_t>((size_t)66 * ws->dots_grid_max,
+                                               (size_t)b2a::kSweepBarriers * b2a::kSweepPartRegion) * es);
   const size_t o_part2 = carve(sizeof(double) * ws->upd_grid_max);
   const size_t o_state = carve(sizeof(b2a::SweepState));
-  const size_t o_dQ = carve((size_t)std::max(maxdim * maxdim, 1) * es);
+  // Q of a rotation: packed K x N for the DFMA kernels, MMA B-fragment order (padded) for the DMMA kernel
+  {
+    const size_t inner = es / 8, parts = inner;
+    const size_t frag = (size_t)((maxdim + 3) / 4) * ((inner * maxdim + 7) / 8 + 3) * parts * 32;
+    ws->q_bytes = (std::max<size_t>(frag, (size_t)maxdim * maxdim * inner) * 8 + 255) / 256 * 256;
+  }
+  const size_t o_dQ = carve(ws->q_bytes);
   const size_t o_flag = carve(sizeof(unsigned long long));
+  const size_t o_xt = carve(sizeof(unsigned int) * 32);
   const bool want_trace = getenv("B2A_SWEEP_TRACE") && getenv("B2A_SWEEP_TRACE")[0] == '1';
   const size_t o_trace = carve(want_trace ? sizeof(unsigned long long) * b2a::kSweepTraceSlots * ctx->num_sms : 8);
   CUDA_TRY(dev_alloc(ctx, &ws->arena, off));
@@ -2023,10 +2476,17 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
   ws->state = reinterpret_cast<b2a::SweepState *>(base + o_state);
   ws->dQ = base + o_dQ;
   ws->sweep_flag = reinterpret_cast<unsigned long long *>(base + o_flag);
+  ws->xchg_ticket = reinterpret_cast<unsigned int *>(base + o_xt);
   ws->sweep_trace = want_trace ? reinterpret_cast<unsigned long long *>(base + o_trace) : nullptr;
-  const size_t want = (size_t)m1 * maxdim * es + sizeof(int) * (m1 + 1) + sizeof(b2a::SweepState) + 64;
+  ws->qpin_off = ((size_t)m1 * maxdim * es + sizeof(int) * (m1 + 1) + sizeof(b2a::SweepState) + 64 + 255) / 256 * 256;
+  const size_t want = ws->qpin_off + 2 * ws->q_bytes;
   CUDA_TRY(pinned_get(ctx, want, &ws->pinned, &ws->pinned_bytes));
+  for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreateWithFlags(&ws->qev[i], cudaEventDisableTiming));
+  if (const char *e = getenv("B2A_ROTATE")) ws->rotate_mode = e[0] != '0';
   B2A_TRY(peer_setup(ctx, ws));
+  // staged exchange: default whenever the peer block is available (B2A_XCHG=0: push from the normalising kernel)
+  ws->xchg_staged = ws->peer.P > 1 && ws->peer_x && !(getenv("B2A_XCHG") && getenv("B2A_XCHG")[0] == '0');
+  if (const char *e = getenv("B2A_XCHG_SM")) ws->xchg_sm = std::max(0, atoi(e));
   if (ctx->world > 1 && (ws->peer.P == 1 || !ws->peer_x)) {  // NCCL all-gather needs its own gather buffer
     const int64_t nx = ws->uniform_partition ? ws->all_counts[0] * ctx->world : n_global;
     CUDA_TRY(dev_alloc(ctx, &ws->xfull, (size_t)nx * es));
@@ -2044,6 +2504,10 @@ int b2a_ws_create(b2a_ctx *ctx, int dtype, int64_t n_rows_local, int64_t n_globa
   ARG_CHECK(maxdim >= 1, "Krylov dimension must be positive");
   // ArnoldiMethod.jl:62-63
   ARG_CHECK((int64_t)maxdim <= n_global, "Krylov dimension should be less than matrix order.");
+  // the in-place basis rotation stages 16 rows x maxdim columns per pipeline stage, two stages at least
+  // (kernels_rotate_mma.cuh): maxdim <= 879 (Float64) / 439 (ComplexF64)
+  ARG_CHECK((size_t)round_up(maxdim, 4) * 16 * dtype_size(dtype) * 2 + 256 <= eng::kTmaSmemBudget,
+            "Krylov dimension too large for the device basis rotation (limit 879 for Float64, 439 for ComplexF64)");
   b2a_ws *ws = new b2a_ws();
   int s = ws_create_impl(ctx, dtype, n_rows_local, n_global, row_offset, maxdim, ws);
   if (s != B2A_OK) {
@@ -2208,9 +2672,12 @@ int b2a_rotate_basis(b2a_ws *ws, int purge, int k, int maxdim, const void *Q_hos
   }
   ARG_CHECK(ldq >= maxdim, "ldq too small");
   CUDA_TRY(cudaSetDevice(ws->ctx->device));
-  return ws->dtype == B2A_F64
-             ? drv::rotate_basis<double>(ws, purge, k, maxdim, reinterpret_cast<const double *>(Q_host), ldq, stats)
-             : drv::rotate_basis<cplx>(ws, purge, k, maxdim, reinterpret_cast<const cplx *>(Q_host), ldq, stats);
+  B2A_TRY(ws->dtype == B2A_F64
+              ? drv::rotate_basis<double>(ws, purge, k, maxdim, reinterpret_cast<const double *>(Q_host), ldq, stats)
+              : drv::rotate_basis<cplx>(ws, purge, k, maxdim, reinterpret_cast<const cplx *>(Q_host), ldq, stats));
+  CUDA_TRY(cudaStreamSynchronize(ws->ctx->stream));  // synchronous on return (inside partialschur it is not)
+  prof_collect(ws->ctx, nullptr, 0, 0);
+  return B2A_OK;
 }
 
 int b2a_rotate_final(b2a_ws *ws, int nconv, const void *Q_host, int ldq, b2a_stats *stats) {
@@ -2222,9 +2689,12 @@ int b2a_rotate_final(b2a_ws *ws, int nconv, const void *Q_host, int ldq, b2a_sta
   }
   ARG_CHECK(ldq >= nconv, "ldq too small");
   CUDA_TRY(cudaSetDevice(ws->ctx->device));
-  return ws->dtype == B2A_F64
-             ? drv::rotate_final<double>(ws, nconv, reinterpret_cast<const double *>(Q_host), ldq, stats)
-             : drv::rotate_final<cplx>(ws, nconv, reinterpret_cast<const cplx *>(Q_host), ldq, stats);
+  B2A_TRY(ws->dtype == B2A_F64
+              ? drv::rotate_final<double>(ws, nconv, reinterpret_cast<const double *>(Q_host), ldq, stats)
+              : drv::rotate_final<cplx>(ws, nconv, reinterpret_cast<const cplx *>(Q_host), ldq, stats));
+  CUDA_TRY(cudaStreamSynchronize(ws->ctx->stream));
+  prof_collect(ws->ctx, nullptr, 0, 0);
+  return B2A_OK;
 }
 
 int b2a_basis_times(b2a_ws *ws, int nconv, const double *Y, int ldy, double *X, int64_t ldx) {

@@ -52,6 +52,12 @@ template <> __device__ __forceinline__ cdouble ld_cg<cdouble>(const cdouble *p) 
 
 constexpr int kSweepPartStride = 160;  // row stride of the per-CTA partial sums (>= #SMs, multiple of 32)
 constexpr int kSweepCoefs = kTmaMaxCols + 2;  // coefficient vector + its squared norm, per buffer
+// Every grid barrier of a launch (A, B, C) owns its OWN region of per-CTA partial sums: in the single-GPU mode every
+// CTA sums all partials itself AFTER the release flag, so a fast CTA that already stores its partials of the next
+// barrier must not touch what a slow CTA is still reading (write-after-read across barriers).  Regions are re-used
+// only by the next launch, which stream order (griddepcontrol.wait included) separates from this one.
+constexpr int kSweepBarriers = 3;
+constexpr size_t kSweepPartRegion = (size_t)(kTmaMaxCols + 1) * kSweepPartStride;  // elements per barrier region
 
 template <class T> __host__ __device__ constexpr size_t sweep_header_bytes() {
   return 256 + (2 * kSweepCoefs * sizeof(T) + 127) / 128 * 128;  // TmaSmem | ha | hb, ring 128-byte aligned
@@ -313,8 +319,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
   }
   __syncwarp();
   mark(3);
-  sweep_reduce_barrier<T, CPW>(acc, nacc, true, ncols, warp, lane, partials, hb, h2, w1sq_p, &state->ticket[3], flag,
-                               epoch + 2, &sm->is_last, &state->error, pv);
+  sweep_reduce_barrier<T, CPW>(acc, nacc, true, ncols, warp, lane, partials + kSweepPartRegion, hb, h2, w1sq_p,
+                               &state->ticket[3], flag, epoch + 2, &sm->is_last, &state->error, pv);
   mark(4);
 
   const double rsq = *reinterpret_cast<const double *>(&ha[ncols]);
@@ -339,8 +345,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
     __syncwarp();
     mark(5);
     // only the norm is reduced; its result lands in the spare slot hb[kSweepCoefs - 1]
-    sweep_reduce_barrier<T, CPW>(acc, nacc, false, ncols, warp, lane, partials, hb + (kSweepCoefs - 1 - ncols), h2,
-                                 w2sq_p, &state->ticket[4], flag, epoch + 3, &sm->is_last, &state->error, pv);
+    sweep_reduce_barrier<T, CPW>(acc, nacc, false, ncols, warp, lane, partials + 2 * kSweepPartRegion,
+                                 hb + (kSweepCoefs - 1 - ncols), h2, w2sq_p, &state->ticket[4], flag, epoch + 3, &sm->is_last, &state->error, pv);
     mark(6);
     rnorm = wnorm;
     wnorm = sqrt(*reinterpret_cast<const double *>(&hb[kSweepCoefs - 1]));

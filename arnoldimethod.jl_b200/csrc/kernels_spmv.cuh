@@ -56,6 +56,51 @@ __device__ __forceinline__ cdouble ld_hint(const cdouble *p, uint64_t pol) {
   return v;
 }
 
+// ---- coherent gathers for the row-sharded mat-vec -----------------------------------------------
+// When x is the NVLink exchange buffer, peers (or the copy engines) write it while earlier launches of this
+// very kernel may still sit in L1 with the previous step's lines, and a kernel launched early spins on the
+// arrival flags while the data lands.  ld.global.nc requires read-only data for the kernel's lifetime and sits
+// outside the memory model, so those instantiations gather x with L2-coherent loads (ld.global.cg: never served
+// from L1; peer and copy-engine writes land in L2) ordered after the flag's ld.acquire.sys by the CTA barrier.
+__device__ __forceinline__ double ld_coh(const double *p) { return __ldcg(p); }
+__device__ __forceinline__ cdouble ld_coh(const cdouble *p) { return __ldcg(p); }
+__device__ __forceinline__ double ld_coh_hint(const double *p, uint64_t pol) {
+  double v;
+  asm volatile("ld.global.cg.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ cdouble ld_coh_hint(const cdouble *p, uint64_t pol) {
+  cdouble v;
+  asm volatile("ld.global.cg.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+
+// What a mat-vec launch waits for before it gathers from the exchange buffer (peer_comm.cuh):
+//   mode 0  nothing (single GPU, or the rank's own column block read straight from the workspace column)
+//   mode 1  every rank's slice, sequence number taken from the device counter seq_x (push model: the normalising
+//           kernel of the previous step stored the slices)
+//   mode 2  the slice of ONE owner rank, sequence number given by the host (staged exchange: one launch per owner
+//           block, so the mat-vec on the blocks that have arrived overlaps the transfer of the others)
+//   mode 3  the slices of all other ranks, host sequence number (staged exchange, operator not stored by owner block)
+struct XWait {
+  PeerView pv;
+  int mode = 0;
+  int owner = 0;
+  unsigned long long want = 0;
+};
+__device__ __forceinline__ void spmv_wait_x(const XWait &xw) {
+  if (xw.mode == 0) return;
+  if (threadIdx.x == 0) {
+    if (xw.mode == 1)
+      peer_x_wait(xw.pv);
+    else if (xw.mode == 2)
+      peer_x_wait_one(xw.pv, xw.owner, xw.want);
+    else
+      peer_x_wait_others(xw.pv, xw.want);
+  }
+  __syncthreads();
+}
+
 template <int LPR> __device__ __forceinline__ double group_sum_d(double v) {
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -63,17 +108,15 @@ template <int LPR> __device__ __forceinline__ double group_sum_d(double v) {
 }
 
 // HINT: column-blocked mode - A loads evict_first, x gathers evict_last (see header)
-template <class T, int LPR, int U, bool HINT = false>
+// COH : x is the NVLink exchange buffer - coherent gathers, and the launch waits for its slice(s) first
+template <class T, int LPR, int U, bool HINT = false, bool COH = false>
 __global__ void __launch_bounds__(256)
     spmv_csr_vector_kernel(int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
-                           const T *__restrict__ vals, const T *__restrict__ x, T *__restrict__ y,
-                           const int *poison, const __grid_constant__ PeerView pv, int wait_x, int accumulate) {
+                           const T *__restrict__ vals, const T *x, T *__restrict__ y,
+                           const int *poison, const __grid_constant__ XWait xw, int accumulate) {
   pdl_wait();
   if (*poison) return;
-  if (wait_x) {  // multi-GPU: x is pushed by the peers (peer_comm.cuh); wait until every slice has landed
-    if (threadIdx.x == 0) peer_x_wait(pv);
-    __syncthreads();
-  }
+  if (COH) spmv_wait_x(xw);  // multi-GPU: wait until the slice(s) of x this launch gathers from have landed
   const int sub = threadIdx.x & (LPR - 1);
   const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / LPR;
@@ -84,7 +127,10 @@ __global__ void __launch_bounds__(256)
   }
   auto ld_col = [&](const int32_t *p) { return HINT ? ld_hint(p, pol_a) : __ldg(p); };
   auto ld_val = [&](const T *p) { return HINT ? ld_hint(p, pol_a) : ld_ro<T>(p); };
-  auto ld_x = [&](const T *p) { return HINT ? ld_hint(p, pol_x) : ld_ro<T>(p); };
+  auto ld_x = [&](const T *p) {
+    if (COH) return HINT ? ld_coh_hint(p, pol_x) : ld_coh(p);
+    return HINT ? ld_hint(p, pol_x) : ld_ro<T>(p);
+  };
 
   // loop bound uniform over the grid (rbase0 is the same for every thread) so that all lanes of a
   // warp reach the full-mask shuffles; rows past the end are predicated off
@@ -141,22 +187,22 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-template <class T>
+template <class T, bool COH = false>
 __global__ void __launch_bounds__(256)
     spmv_csr_scalar_kernel(int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
-                           const T *__restrict__ vals, const T *__restrict__ x, T *__restrict__ y,
-                           const int *poison, const __grid_constant__ PeerView pv, int wait_x) {
+                           const T *__restrict__ vals, const T *x, T *__restrict__ y,
+                           const int *poison, const __grid_constant__ XWait xw, int accumulate) {
   if (*poison) return;
-  if (wait_x) {
-    if (threadIdx.x == 0) peer_x_wait(pv);
-    __syncthreads();
-  }
+  if (COH) spmv_wait_x(xw);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
     const int64_t s = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
     T acc = Scalar<T>::zero();
-    for (int64_t i = s; i < e; ++i) acc = Scalar<T>::fma_(ld_ro<T>(vals + i), ld_ro<T>(x + __ldg(colind + i)), acc);
-    y[r] = acc;
+    for (int64_t i = s; i < e; ++i) {
+      const T xv = COH ? ld_coh(x + __ldg(colind + i)) : ld_ro<T>(x + __ldg(colind + i));
+      acc = Scalar<T>::fma_(ld_ro<T>(vals + i), xv, acc);
+    }
+    y[r] = accumulate ? Scalar<T>::add(y[r], acc) : acc;
   }
 }
 

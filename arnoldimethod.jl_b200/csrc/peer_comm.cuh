@@ -31,6 +31,9 @@ struct PeerView {
   int slot = 0;                         // doubles per rank slot
   char *peer[kPeerMaxRanks] = {nullptr};  // base of every rank's communication block (peer[rank] = local)
   unsigned long long off_flag_ar = 0, off_data_ar = 0, off_flag_x = 0, off_x = 0;
+  // staged exchange (copy engines / per-owner flags): its own flag array, and a second x buffer (exchange number
+  // parity selects the buffer, so a rank that runs one mat-vec ahead never overwrites what a peer still reads)
+  unsigned long long off_flag_xs = 0, x_stride = 0;
   unsigned long long *seq_ar = nullptr;  // local device counters
   unsigned long long *seq_x = nullptr;
   int *err = nullptr;
@@ -119,6 +122,24 @@ __device__ __forceinline__ void peer_x_wait(const PeerView &pv) {  // one thread
       }
     }
   }
+}
+
+// staged exchange: wait for the slice of ONE owner rank; `want` is the host's exchange counter (every exchange
+// publishes, poisoned sweeps included, so host and device never drift)
+__device__ __forceinline__ void peer_x_wait_one(const PeerView &pv, int owner, unsigned long long want) {
+  const unsigned long long *f = reinterpret_cast<const unsigned long long *>(pv.peer[pv.rank] + pv.off_flag_xs) + owner;
+  unsigned long long spins = 0;
+  while (ld_acquire_sys(f) < want) {
+    if (++spins > kPeerSpinLimit) {
+      *pv.err = 3;
+      break;
+    }
+  }
+}
+// ... or for the slices of all other ranks (operators that are not stored by owner block)
+__device__ __forceinline__ void peer_x_wait_others(const PeerView &pv, unsigned long long want) {
+  for (int p = 0; p < pv.P; ++p)
+    if (p != pv.rank) peer_x_wait_one(pv, p, want);
 }
 
 }  // namespace b2a
