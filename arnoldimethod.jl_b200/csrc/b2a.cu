@@ -252,6 +252,7 @@ struct b2a_op {
   bool owns = true;
   int lpr = 8;  // lanes per row (column)
   int rows_in_flight = 2, grid_mult = 16;  // SpMV tuning (env B2A_SPMV_U / B2A_SPMV_GRID)
+  int entries_in_flight = 4;               // entries per lane and row issued together (B2A_SPMV_E = 1, 2, 4)
   // TMA-stream kernel: row tiles built at upload (kernels_spmv_tma.cuh)
   int32_t *d_tile_row = nullptr;
   int ntiles = 0, tma_stages = 0;
@@ -324,6 +325,7 @@ struct b2a_ws {
   cudaEvent_t qev[2] = {nullptr, nullptr};
   bool q_used[2] = {false, false};
   int q_slot = 0;
+  int rot_ctas = 0;     // CTAs per SM of the DMMA rotation: 0 = automatic (B2A_ROT_CTAS)
   int rotate_mode = 1;  // 1 = TMA + DMMA kernel (kernels_rotate_mma.cuh), 0 = shared-memory DFMA kernels (B2A_ROTATE=0)
   int tune_rt_dots = 0, tune_rt_upd = 0, tune_stages = 0, tune_ctas = 1, tune_l2promo = 2;  // experiment overrides (env)
 };
@@ -758,19 +760,24 @@ static double op_bytes(const b2a_op *A);
 using b2a::XWait;
 
 // vector kernel, one launch: rowptr / accumulate select the column block, xw what the launch waits for
-template <class DT, int LPR, int U, bool HINT, bool COH>
+template <class DT, int LPR, int U, bool HINT, bool COH, int E = 4>
 static cudaError_t launch_spmv_vec_one(b2a_op *A, const int64_t *rowptr, const DT *x, DT *y, const int *poison,
                                        cudaStream_t st, int sms, const XWait &xw, int accumulate) {
   const int64_t threads = cdiv(A->n_local, U) * LPR;
   const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)sms * A->grid_mult, cdiv(threads, 256)));
-  return launch_pdl(b2a::spmv_csr_vector_kernel<DT, LPR, U, HINT, COH>, (unsigned)grid, 256u, 0, st, A->n_local, rowptr,
-                    (const int32_t *)A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y, poison, xw, accumulate);
+  return launch_pdl(b2a::spmv_csr_vector_kernel<DT, LPR, U, HINT, COH, E>, (unsigned)grid, 256u, 0, st, A->n_local,
+                    rowptr, (const int32_t *)A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y, poison, xw,
+                    accumulate);
 }
 template <class DT, int LPR, int U>
 static cudaError_t launch_spmv_vec_u(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms,
                                      const XWait &xw) {
   if (xw.mode) return launch_spmv_vec_one<DT, LPR, 2, false, true>(A, A->d_ptr, x, y, poison, st, sms, xw, 0);
-  return launch_spmv_vec_one<DT, LPR, U, false, false>(A, A->d_ptr, x, y, poison, st, sms, xw, 0);
+  switch (A->entries_in_flight) {  // B2A_SPMV_E (experiments); results are bit-identical for every E
+    case 1: return launch_spmv_vec_one<DT, LPR, U, false, false, 1>(A, A->d_ptr, x, y, poison, st, sms, xw, 0);
+    case 2: return launch_spmv_vec_one<DT, LPR, U, false, false, 2>(A, A->d_ptr, x, y, poison, st, sms, xw, 0);
+    default: return launch_spmv_vec_one<DT, LPR, U, false, false, 4>(A, A->d_ptr, x, y, poison, st, sms, xw, 0);
+  }
 }
 // column-blocked operator (x larger than L2): one pass per block, L2-hinted loads, the first pass writes y, the
 // others accumulate; every pass gathers from the same x, so only the first one waits
@@ -824,7 +831,6 @@ static cudaError_t launch_spmv_vec(b2a_op *A, const DT *x, DT *y, const int *poi
   switch (A->rows_in_flight) {
     case 1: return launch_spmv_vec_u<DT, LPR, 1>(A, x, y, poison, st, sms, xw);
     case 4: return launch_spmv_vec_u<DT, LPR, 4>(A, x, y, poison, st, sms, xw);
-    case 8: return launch_spmv_vec_u<DT, LPR, 8>(A, x, y, poison, st, sms, xw);
     default: return launch_spmv_vec_u<DT, LPR, 2>(A, x, y, poison, st, sms, xw);
   }
 }
@@ -1121,7 +1127,7 @@ template <class DT> static bool try_rotate2(b2a_ws *ws, int col0, int K, int N, 
 // ---- TMA + DMMA rotation (kernels_rotate_mma.cuh) ------------------------------------------------------------
 struct RotPlan {
   b2a::RotGeom g;
-  int NT = 4, NCH = 1, KS = 1, b_in_smem = 1, grid = 1;
+  int NT = 4, NCH = 1, KS = 1, b_in_smem = 1, grid = 1, ctas = 1;
   size_t smem = 0, b_elems = 0;
 };
 // Largest row tile (16 rows per consumer warp) that leaves at least two ring stages, Q fragments in shared memory
@@ -1145,7 +1151,13 @@ static bool rot_plan(const b2a_ws *ws, int K, int N, bool cplx, RotPlan *p) {
   const int box_cols = (int)round_up(cdiv(K, nbox), 4);
   const int kpad = nbox * box_cols;
   const size_t b_bytes = (p->b_elems * 8 + 127) / 128 * 128;
-  const size_t budget = kTmaSmemBudget - 256;
+  // two CTAs per SM (16 consumer warps to cover tile-boundary bubbles) when two full-size tiles with two stages each
+  // and Q fit twice; else one CTA with a deeper ring.  B2A_ROT_CTAS = 1 / 2 forces.
+  int want_ctas = ws->rot_ctas;
+  const size_t full_tile = (size_t)kpad * 128 * inner * 8;
+  if (want_ctas == 0) want_ctas = (2 * full_tile + b_bytes + 256 + 1024 <= kTmaSmemBudget / 2) ? 2 : 1;
+  p->ctas = want_ctas;
+  const size_t budget = kTmaSmemBudget / want_ctas - 256 - (want_ctas > 1 ? 1024 : 0);
   const int order[8][2] = {{1, 8}, {1, 4}, {0, 8}, {0, 4}, {1, 2}, {0, 2}, {1, 1}, {0, 1}};
   for (const auto &o : order) {
     const int bsm = o[0], warps = o[1], R = 16 * warps;
@@ -1157,7 +1169,7 @@ static bool rot_plan(const b2a_ws *ws, int K, int N, bool cplx, RotPlan *p) {
     if (stages < 2) continue;
     const int64_t ntiles = cdiv(std::max<int64_t>(ws->n_local, 1), R);
     if (ntiles > 2000000000LL) return false;
-    int gr = (int)std::min<int64_t>(ws->ctx->num_sms, ntiles);
+    int gr = (int)std::min<int64_t>((int64_t)ws->ctx->num_sms * want_ctas, ntiles);
     const int tpc = (int)cdiv(ntiles, gr);
     gr = (int)cdiv(ntiles, tpc);
     stages = std::min(stages, std::max(2, tpc));
@@ -1217,16 +1229,22 @@ template <> void pack_b_fragments<cplx>(const cplx *Qp, int K, int N, const RotP
       }
 }
 
-template <bool CPLX, int NT>
-static int launch_rotate_mma_inst(b2a_ws *ws, const CUtensorMap &tm, int col0, int N, const RotPlan &p, int move_src,
-                                  int move_dst) {
-  auto kern = b2a::rotate_mma_kernel<CPLX, NT>;
-  B2A_TRY(ensure_smem_attr(ws->ctx, kern, kTmaSmemBudget));
+template <bool CPLX, int NT, int MINB>
+static int launch_rotate_mma_inst2(b2a_ws *ws, const CUtensorMap &tm, int col0, int N, const RotPlan &p, int move_src,
+                                   int move_dst) {
+  auto kern = b2a::rotate_mma_kernel<CPLX, NT, MINB>;
+  B2A_TRY(ensure_smem_attr(ws->ctx, kern, kTmaSmemBudget / MINB));
   kern<<<(unsigned)p.grid, b2a::kRotThreads, p.smem, ws->ctx->stream>>>(
       tm, reinterpret_cast<double *>(ws->dV), ws->ld, col0, N, reinterpret_cast<const double *>(ws->dQ), p.KS, p.NCH,
       p.g, move_src, move_dst, p.b_in_smem);
   CUDA_TRY(cudaGetLastError());
   return B2A_OK;
+}
+template <bool CPLX, int NT>
+static int launch_rotate_mma_inst(b2a_ws *ws, const CUtensorMap &tm, int col0, int N, const RotPlan &p, int move_src,
+                                  int move_dst) {
+  if (p.ctas > 1) return launch_rotate_mma_inst2<CPLX, NT, 2>(ws, tm, col0, N, p, move_src, move_dst);
+  return launch_rotate_mma_inst2<CPLX, NT, 1>(ws, tm, col0, N, p, move_src, move_dst);
 }
 
 // host -> device copy of a small array through one of the two pinned Q slots, no stream synchronisation
@@ -1712,6 +1730,7 @@ static int upload_index(b2a_ctx *ctx, const void *host, int64_t count, int idx_w
 static void op_tuning(b2a_op *op) {
   if (const char *e = getenv("B2A_SPMV_U")) op->rows_in_flight = atoi(e);
   if (const char *e = getenv("B2A_SPMV_GRID")) op->grid_mult = std::max(1, atoi(e));
+  if (const char *e = getenv("B2A_SPMV_E")) op->entries_in_flight = atoi(e);
   if (const char *e = getenv("B2A_SPMV_LPR")) op->lpr = atoi(e);
   if (const char *e = getenv("B2A_SPMV_STAGES")) op->tma_stages = atoi(e);
 }
@@ -2483,6 +2502,7 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
   CUDA_TRY(pinned_get(ctx, want, &ws->pinned, &ws->pinned_bytes));
   for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreateWithFlags(&ws->qev[i], cudaEventDisableTiming));
   if (const char *e = getenv("B2A_ROTATE")) ws->rotate_mode = e[0] != '0';
+  if (const char *e = getenv("B2A_ROT_CTAS")) ws->rot_ctas = std::max(0, std::min(2, atoi(e)));
   B2A_TRY(peer_setup(ctx, ws));
   // staged exchange: default whenever the peer block is available (B2A_XCHG=0: push from the normalising kernel)
   ws->xchg_staged = ws->peer.P > 1 && ws->peer_x && !(getenv("B2A_XCHG") && getenv("B2A_XCHG")[0] == '0');

@@ -19,8 +19,10 @@
 //   * ComplexF64 runs as the real product [Vre Vim] * [[Qre Qim], [-Qim Qre]] on the interleaved (re, im) tile:
 //     the re / im parts of one 16-byte element feed two MMAs against the two matching B fragments, and an
 //     accumulator pair IS one complex output element.
-//   * the column move V[:, k+1] <- V[:, maxdim+1] of run.jl:365 rides along (consumer warps, after the tile is in
-//     shared memory: the destination column is one of the inputs).
+//   * the column move V[:, k+1] <- V[:, maxdim+1] of run.jl:365 rides along in a dedicated MOVER warp (after the
+//     tile is in shared memory: the destination column is one of the inputs).  First version: the consumer warps
+//     did it at the top of every tile, and the dependent LDG -> STG pair (HBM latency, ~1 us) was 20 % of all
+//     stall samples and starved the tensor pipe (ncu r2: dmma pipe 43 %, DRAM 46 %).
 //
 // Everything is read once and written once: n s (K + N + 2) bytes, B_rot of SURVEY 8(d).
 #pragma once
@@ -30,7 +32,7 @@
 namespace b2a {
 
 constexpr int kRotConsumerWarps = 8;
-constexpr int kRotThreads = (kRotConsumerWarps + 1) * 32;
+constexpr int kRotThreads = (kRotConsumerWarps + 2) * 32;  // + producer warp + mover warp
 
 struct RotGeom {
   int R;              // rows per tile = 16 * warps
@@ -50,8 +52,8 @@ __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
 }
 
 // V is addressed in doubles: element (row, col, part) of the workspace at (col * ld + row) * inner + part.
-template <bool CPLX, int NT>
-__global__ void __launch_bounds__(kRotThreads, 1)
+template <bool CPLX, int NT, int MINB>
+__global__ void __launch_bounds__(kRotThreads, MINB)
     rotate_mma_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ V, int64_t ld, int col0, int N,
                       const double *__restrict__ Bg, int KS, int NCH, RotGeom g, int move_src, int move_dst,
                       int b_in_smem) {
@@ -72,7 +74,7 @@ __global__ void __launch_bounds__(kRotThreads, 1)
     tma_prefetch_desc(&tmap);
     for (int s = 0; s < g.stages; ++s) {
       mbar_init(&sm->full[s], 1);
-      mbar_init(&sm->empty[s], g.warps);
+      mbar_init(&sm->empty[s], g.warps + 1);  // consumer warps + the mover
     }
     mbar_fence_init();
   }
@@ -98,7 +100,35 @@ __global__ void __launch_bounds__(kRotThreads, 1)
     }
     return;
   }
-  if (warp >= g.warps) return;
+  if (warp == kRotConsumerWarps + 1) {
+    // ------------------------------------------------------------------ mover: V[rows, move_dst] <- V[rows, move_src]
+    // The destination column is an INPUT of the product, so its rows may be overwritten only once the tile that
+    // holds them sits in shared memory (full barrier).  The mover releases the stage at once (it never reads it) and
+    // takes the HBM latency of the copy off the consumers' critical path.
+    const int pieces = g.R * INNER / 2;  // 16-byte pieces per tile column
+    for (int l = 0; l < ntl; ++l) {
+      const int s = l % g.stages;
+      mbar_wait(&sm->full[s], ((uint32_t)(l / g.stages)) & 1u);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm->empty[s]);
+      if (move_dst >= 0) {
+        const int64_t off = (int64_t)(first + l) * g.R * INNER;
+        const double2 *src = reinterpret_cast<const double2 *>(V + (int64_t)move_src * ld * INNER + off);
+        double2 *dst = reinterpret_cast<double2 *>(V + (int64_t)move_dst * ld * INNER + off);
+        double2 x[4];  // R * INNER / 2 <= 128 pieces = 4 per lane
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (lane + 32 * u < pieces) x[u] = src[lane + 32 * u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (lane + 32 * u < pieces) dst[lane + 32 * u] = x[u];
+      }
+    }
+    return;
+  }
+  if (warp >= g.warps) {
+    return;
+  }
 
   // ---------------------------------------------------------------------- consumers
   const int gq = lane >> 2, tq = lane & 3;  // MMA group id (row of A / column of B) and thread-in-group (k slot)
@@ -109,15 +139,6 @@ __global__ void __launch_bounds__(kRotThreads, 1)
     mbar_wait(&sm->full[s], ((uint32_t)(l / g.stages)) & 1u);
     const double *tile = ring + (size_t)s * stage_elems;
     const int64_t row0 = (int64_t)(first + l) * g.R;
-    if (move_dst >= 0) {
-      // V[rows, move_dst] <- V[rows, move_src]: 16 rows per warp = 8 (real) / 16 (complex) 16-byte pieces
-      constexpr int PIECES = 8 * INNER;
-      if (lane < PIECES) {
-        const int64_t off = (row0 + 16 * warp) * INNER + 2 * lane;
-        const double2 x = *reinterpret_cast<const double2 *>(V + (int64_t)move_src * ld * INNER + off);
-        *reinterpret_cast<double2 *>(V + (int64_t)move_dst * ld * INNER + off) = x;
-      }
-    }
     for (int ch = 0; ch < NCH; ++ch) {
       double acc[2][NT][2];
 #pragma unroll

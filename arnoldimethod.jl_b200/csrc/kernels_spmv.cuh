@@ -109,7 +109,11 @@ template <int LPR> __device__ __forceinline__ double group_sum_d(double v) {
 
 // HINT: column-blocked mode - A loads evict_first, x gathers evict_last (see header)
 // COH : x is the NVLink exchange buffer - coherent gathers, and the launch waits for its slice(s) first
-template <class T, int LPR, int U, bool HINT = false, bool COH = false>
+// E   : entries in flight per lane and row.  The gathers are latency-bound (ncu r1b: long-scoreboard 35 of 44 stall
+//       cycles per issue, L2 at 70 % of its sector rate), and a lane that walks its row one entry at a time serialises
+//       (column index -> gather) round trips; with E = 4 a lane group of LPR = 4 has a whole 16-entry row in flight
+//       at once.  Entries are still accumulated in ascending order, so the result is bit-identical for every E.
+template <class T, int LPR, int U, bool HINT = false, bool COH = false, int E = 4>
 __global__ void __launch_bounds__(256)
     spmv_csr_vector_kernel(int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
                            const T *__restrict__ vals, const T *x, T *__restrict__ y,
@@ -147,28 +151,47 @@ __global__ void __launch_bounds__(256)
         rs[u] = re[u] = 0;
       }
     }
-    // first LPR entries of each of the U rows: all loads issued before any use
-    int32_t c[U];
-    T a[U];
+    // first E * LPR entries of each of the U rows: all index / value loads issued before any gather
+    int32_t c[U][E];
+    T a[U][E];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t i = rs[u] + sub;
-      const bool ok = i < re[u];
-      c[u] = ok ? ld_col(colind + i) : 0;
-      a[u] = ok ? ld_val(vals + i) : Scalar<T>::zero();
-    }
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int64_t i = rs[u] + sub + e * LPR;
+        const bool ok = i < re[u];
+        c[u][e] = ok ? ld_col(colind + i) : -1;
+        a[u][e] = ok ? ld_val(vals + i) : Scalar<T>::zero();
+      }
     T acc[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const bool ok = rs[u] + sub < re[u];
-      const T xv = ok ? ld_x(x + c[u]) : Scalar<T>::zero();
-      acc[u] = Scalar<T>::mul(a[u], xv);
+      T xv[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) xv[e] = c[u][e] >= 0 ? ld_x(x + c[u][e]) : Scalar<T>::zero();
+      acc[u] = Scalar<T>::mul(a[u][0], xv[0]);
+#pragma unroll
+      for (int e = 1; e < E; ++e) acc[u] = Scalar<T>::fma_(a[u][e], xv[e], acc[u]);
     }
-    // rows longer than LPR
+    // rows longer than E * LPR: further chunks of E entries per lane
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      for (int64_t i = rs[u] + sub + LPR; i < re[u]; i += LPR)
-        acc[u] = Scalar<T>::fma_(ld_val(vals + i), ld_x(x + ld_col(colind + i)), acc[u]);
+      for (int64_t i0 = rs[u] + sub + E * LPR; i0 < re[u]; i0 += E * LPR) {
+        int32_t cc[E];
+        T aa[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int64_t i = i0 + e * LPR;
+          const bool ok = i < re[u];
+          cc[e] = ok ? ld_col(colind + i) : -1;
+          aa[e] = ok ? ld_val(vals + i) : Scalar<T>::zero();
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const T xv = cc[e] >= 0 ? ld_x(x + cc[e]) : Scalar<T>::zero();
+          acc[u] = Scalar<T>::fma_(aa[e], xv, acc[u]);
+        }
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {

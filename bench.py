@@ -20,7 +20,10 @@ of h / norms and an all-gather of x per step; `value` is then (global steps/s) x
 --impl reference: the reference's own CPU path.  Julia is not in the image, so this is the
 oracle port (NumPy/SciPy restatement, see oracle/__init__.py) on the host cores: SciPy CSR
 mat-vec (single-threaded like Julia's SparseArrays.mul!) + OpenBLAS gemv/gemm/nrm2 on all
-cores.  Each step is a bounded sample: the same matrix and start vector, restarts capped at 1.
+cores.  Each step is the SAME complete solve as the GPU arm's step (same matrix, start vector, tolerance; to
+convergence: 81 Arnoldi steps, 5 restarts, about 6 s per step on 16 cores), so both arms share one `config`;
+warm-up steps are capped at one restart (untimed).  At N > 1 the CPU arm still solves ONE shard-sized problem: `value`
+counts shard-steps (a step on an N-shard matrix = N shard-steps, CPU time per step being linear in n).
 """
 
 import argparse
@@ -72,14 +75,19 @@ def make_v1(n_global, row_offset, n_local, seed=1):
     return rng.random(n_local)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of
-# this workload (profiles/r1b_ncu_full_summary.txt); None where no capture exists.  The bytes of the fused
-# sweep kernel depend on j and on whether its gated phase ran, so its entry is the measured ratio
-# traffic / algorithmic bytes of the two captured launches (j = 39 without, j = 40 with second pass:
-# 568.6 / 664 MB and 830.5 / 1016 MB - below 1 because the ring is re-used across the phases and the
-# backward pass finds the tail of the panel in L2), applied to the average algorithmic bytes per launch.
-NCU_TRAFFIC_BYTES = {"spmv": 216.5e6}
-NCU_TRAFFIC_RATIO = {"cgs_sweep": 0.833}
+NCU_TRAFFIC_FILE = os.path.join("profiles", "ncu_traffic.json")
+
+
+def ncu_traffic_table():
+    """{kernel kind: dram bytes / algorithmic bytes} from the committed summary of the `ncu --set full` captures
+    (profiles/ncu_traffic.json names the .txt summaries it was read from).  bench.py cannot run ncu inside the timed
+    process, so `roofline.traffic` = this measured ratio x the algorithmic bytes per launch measured live."""
+    try:
+        return json.load(open(os.path.join(ROOT, NCU_TRAFFIC_FILE)))
+    except Exception:
+        return {}
+
+
 LIMITER_NOTES = {
     "spmv": "uniformly random columns: every 8-byte gather of x moves a 32-byte sector through L2->L1; ncu: "
             "lts__throughput 70 %, l1tex__throughput 72 % of peak, DRAM traffic == algorithmic bytes. "
@@ -89,6 +97,8 @@ LIMITER_NOTES = {
                  "run at 6.0-6.5 TB/s, the rest is 2-3 in-kernel grid barriers (~4 us each) and the launch",
     "cgs_update": "HBM stream of the Krylov panel through a TMA ring (fused update + speculative dots)",
     "cgs_dots": "HBM stream of the Krylov panel through a TMA ring",
+    "rotate": "in-place V <- V Q: TMA ring + FP64 tensor pipe (DMMA.8x8x4), HBM / FP64 ridge",
+    "xchg": "NVLink: staged copy-engine exchange of x, hidden behind the owner-blocked mat-vec",
 }
 
 
@@ -179,9 +189,9 @@ def run_reference(args):
     n = N_PER_GPU  # bounded sample: one GPU's shard-sized problem, restarts capped
     indptr, indices, data = make_shard(n, 0, n)
     v1 = make_v1(n, 0, n)
-    restarts = 1
+    restarts = 200  # to convergence, exactly the GPU arm's step (5 restarts, 81 Arnoldi steps)
     for _ in range(args.warmup):
-        oracle_run(indptr, indices, data, n, v1, restarts)
+        oracle_run(indptr, indices, data, n, v1, 1)  # untimed warm-up: one restart is enough to page everything in
     t_tot, mv_tot, timers = 0.0, 0, {}
     for _ in range(args.steps):
         hist, dt = oracle_run(indptr, indices, data, n, v1, restarts)
@@ -191,14 +201,15 @@ def run_reference(args):
             timers[k] = timers.get(k, 0.0) + v
     value = mv_tot / t_tot
     cores = host_threads()
-    sample = (f"same matrix (n=1e6, 16 nnz/row, designed top spectrum) and start vector; each step = "
-              f"partialschur with restarts capped at {restarts} ({mv_tot // max(args.steps, 1)} Arnoldi steps); "
-              f"SciPy CSR matvec 1 thread (as Julia SparseArrays.mul!), OpenBLAS gemv/gemm on {cores} threads")
+    sample = (f"same matrix (n=1e6, 16 nnz/row, designed top spectrum), start vector and tolerance as the GPU arm; each "
+              f"step = the complete partialschur solve to convergence ({mv_tot // max(args.steps, 1)} Arnoldi steps, "
+              f"{hist.restarts_done} restarts); SciPy CSR matvec 1 thread (as Julia SparseArrays.mul!), OpenBLAS "
+              f"gemv/gemm on {cores} threads; at N > 1 still ONE shard-sized problem (value counts shard-steps)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(1, restarts_cap=restarts),
+        "config": workload_config(max(1, args.gpus), mv=mv_tot // max(args.steps, 1), restarts=hist.restarts_done),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "phase_seconds": {k: round(v, 3) for k, v in timers.items()}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -212,6 +223,12 @@ def workload_config(n_gpus, restarts_cap=None, mv=None, restarts=None):
     cfg = {
         "workload": "BASELINE cfg2: random CSR Float64, n=1e6 rows/GPU, 16 nnz/row, designed top spectrum "
                     "(d_i = 5+20*0.9^i, i<40); partialschur nev=20 mindim=20 maxdim=40 which=LM tol=1e-6",
+        "mode": "designed-spectrum solve to CONVERGENCE (restarts cap 200; SURVEY 8(d)'s parity matrix), not the "
+                "fixed-10-restart run on the pure-random matrix: the per-step work is the same, and the solve can be "
+                "checked (converged, residual)",
+        "restarts_cap": 200,
+        "step_unit": "value = Arnoldi steps/s x n_gpus (1e6-row shard-steps/s); the CPU arm solves one shard-sized "
+                     "problem at every N",
         "n_global": N_PER_GPU * n_gpus, "nnz_global": N_PER_GPU * n_gpus * NNZ_PER_ROW,
         "nev": NEV, "mindim": MINDIM, "maxdim": MAXDIM, "which": WHICH, "tol": TOL,
         "parallelism": f"row-sharded x{n_gpus}" if n_gpus > 1 else "single GPU",
@@ -351,10 +368,12 @@ def run_gpu(args):
                     "share_of_kernel_time": round(kern[top]["ms"] / total_ms, 3),
                     "algo_bytes_per_launch": kern[top]["algo_bytes_per_launch"],
                     "avg_launch_us": kern[top]["avg_us"], "kernels": kern}
-        roofline["traffic"] = NCU_TRAFFIC_BYTES.get(top)
-        if roofline["traffic"] is None and top in NCU_TRAFFIC_RATIO:
-            roofline["traffic"] = round(NCU_TRAFFIC_RATIO[top] * kern[top]["algo_bytes_per_launch"], 1)
-            roofline["traffic_source"] = "ncu ratio traffic/algorithmic of two captured launches x average algorithmic bytes"
+        tt = ncu_traffic_table().get(top)
+        if tt:
+            roofline["traffic"] = round(tt["dram_over_algorithmic"] * kern[top]["algo_bytes_per_launch"], 1)
+            roofline["traffic_source"] = (f"{NCU_TRAFFIC_FILE}: dram__bytes_read+write / algorithmic bytes = "
+                                          f"{tt['dram_over_algorithmic']} ({tt['source']}) x the algorithmic bytes "
+                                          f"per launch measured in this run")
         roofline["limiter"] = LIMITER_NOTES.get(top)
         # context: the HBM-streaming Gram-Schmidt sweeps (dots + update) taken together, and all kernels
         gs = [prof[k] for k in ("cgs_dots", "cgs_update", "cgs_sweep") if k in prof and prof[k]["launches"]]
@@ -403,14 +422,29 @@ def run_gpu(args):
     h2d = indptr_p.nbytes + indices_p.nbytes + data_p.nbytes + v1_p.nbytes
     d2h = int(Q.nbytes + R.nbytes + lam.nbytes)
 
-    # residual check of the e2e result (independent SciPy mat-vec; single GPU only, off the clock)
-    resid = None
-    if world == 1:
-        import scipy.sparse as sp
+    # residual ||A Q - Q R||_F of the e2e result with an INDEPENDENT SciPy mat-vec, off the clock.  N > 1: every rank
+    # gathers the Schur vectors (NCCL all-gather of the row blocks), multiplies its own row shard of A on the host and
+    # the squared norms of the row blocks are summed over the ranks.
+    import scipy.sparse as sp
 
-        A = sp.csr_matrix((data, indices, indptr), shape=(n_global, n_global))
-        Qc = np.array(Q)
-        resid = float(np.linalg.norm(A @ Qc - Qc @ R))
+    Qc = np.ascontiguousarray(np.array(Q))
+    if world > 1:
+        parts = [torch.empty((n_local, Qc.shape[1]), dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(parts, torch.from_numpy(Qc).cuda())
+        Qfull = torch.cat(parts).cpu().numpy()
+        del parts
+    else:
+        Qfull = Qc
+    A_loc = sp.csr_matrix((data, indices, indptr), shape=(n_local, n_global))
+    sq = torch.tensor([float(np.linalg.norm(A_loc @ Qfull - Qc @ R) ** 2),
+                       float(np.linalg.norm(Qfull.T @ Qfull - np.eye(Qfull.shape[1])) ** 2)],
+                      dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(sq)
+        sq[1] /= world  # the orthogonality defect was computed redundantly by every rank
+    resid = float(np.sqrt(sq[0].item()))
+    ortho = float(np.sqrt(sq[1].item()))
+    del Qfull
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -443,7 +477,7 @@ def run_gpu(args):
             "hbm_frac_aggregate": round(hbm_gbs / (peak * world), 4),
             "converged": converged, "nconverged": int(last_hist.nconverged),
             "second_pass_rate": round(last_hist.stats["second_passes"] / max(last_hist.mvproducts, 1), 3),
-            "residual_AQ_QR": resid,
+            "residual_AQ_QR": resid, "residual_bound_n_tol": n_global * TOL, "orthogonality_QtQ_I": ortho,
             "host_ms_per_step": {k: round(v, 3) for k, v in last_hist.timers_ms.items()},
         }
         print(json.dumps(line), flush=True)

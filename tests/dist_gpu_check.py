@@ -4,7 +4,15 @@
         --master-port 29511 tests/dist_gpu_check.py
 
 Row-sharded partialschur over NCCL must give the same H / eigenvalues as the oracle run on the
-whole matrix (shard-count invariance), for Float64 and ComplexF64.  Prints DIST_GPU_CHECK_OK."""
+whole matrix (shard-count invariance), for Float64 and ComplexF64.  Prints DIST_GPU_CHECK_OK.
+
+    ... tests/dist_gpu_check.py --big [rows_per_gpu]
+
+BASELINE-size variant (default 1e6 rows per GPU, bench.py's cfg-2 matrix, any world size): the first sweep's H
+against the oracle (<= 1e-13 relative), then the complete solve: `mvproducts` within one restart of the oracle's,
+eigenvalues <= 10 tol |lambda|, ||A Q - Q R|| <= n tol with an independent SciPy mat-vec of the gathered Schur
+vectors, ||Q'Q - I||.  Rank 0 builds the whole matrix for the oracle; the GPUs only ever see their own shard.
+Prints one JSON line and DIST_GPU_BIG_OK."""
 
 import os
 import sys
@@ -20,12 +28,92 @@ import b200arnoldi as b2a
 import oracle
 
 
+def big(ctx, rank, world, rows_per_gpu):
+    import json
+    import time
+
+    import bench
+    from arnoldimethod_jl_b200 import _lib as L
+    from arnoldimethod_jl_b200.api import _run
+
+    bench.N_PER_GPU = rows_per_gpu  # make_shard keys its generator by row block
+    n = rows_per_gpu * world
+    off = rank * rows_per_gpu
+    indptr, indices, data = bench.make_shard(n, off, rows_per_gpu)
+    v1 = bench.make_v1(n, off, rows_per_gpu)
+    op = b2a.Operator.from_csr_arrays(ctx, indptr, indices, data, n, row_offset=off)
+    ws = b2a.ArnoldiWorkspace(rows_per_gpu, bench.MAXDIM, ctx=ctx, n_global=n, row_offset=off)
+    assert os.environ.get("B2A_NO_PEER") == "1" or ws.comm_mode == "peer", ws.comm_mode
+    out = dict(world=world, n=n, rows_per_gpu=rows_per_gpu, collectives=ws.comm_mode,
+               env={k: v for k, v in os.environ.items() if k.startswith("B2A_")})
+
+    # --- first sweep: H against the oracle
+    steps = 20
+    ws.set_col(1, v1)
+    ws.reinitialize(0, "keep")
+    ws.iterate_arnoldi(op, 1, steps)
+    H = np.array(ws.H)[: steps + 1, :steps].copy()
+    Vl = ws.get_cols(1, steps + 1)
+    t0 = time.time()
+    if rank == 0:
+        blocks = [bench.make_shard(n, r * rows_per_gpu, rows_per_gpu) for r in range(world)]
+        ip = np.concatenate([[0]] + [b[0][1:] + r * rows_per_gpu * bench.NNZ_PER_ROW for r, b in enumerate(blocks)])
+        A = sp.csr_matrix((np.concatenate([b[2] for b in blocks]), np.concatenate([b[1] for b in blocks]), ip), shape=(n, n))
+        v1g = np.concatenate([bench.make_v1(n, r * rows_per_gpu, rows_per_gpu) for r in range(world)])
+        arn = oracle.ArnoldiWorkspace(np.float64, n, bench.MAXDIM)
+        arn.V[:, 0] = v1g / np.linalg.norm(v1g)
+        oracle.iterate_arnoldi(A, arn, 1, steps)
+        Ho = arn.H[: steps + 1, :steps]
+        out["H_relerr_first_sweep"] = float(np.abs(H - Ho).max() / np.abs(Ho).max())
+        out["V_abserr_first_sweep_rank0_rows"] = float(np.abs(Vl - arn.V[:rows_per_gpu, : steps + 1]).max())
+        assert out["H_relerr_first_sweep"] <= 1e-13, out
+        assert out["V_abserr_first_sweep_rank0_rows"] <= 1e-12, out
+        del arn
+
+    # --- the complete solve
+    ws.set_col(1, v1)
+    P, hist = _run(ws, op, bench.NEV, bench.WHICH, bench.TOL, bench.MINDIM, bench.MAXDIM, 200, 1, L.INIT_KEEP, 0)
+    Ql = np.ascontiguousarray(ws.get_cols(1, hist.nconverged))
+    parts = [torch.empty((rows_per_gpu, Ql.shape[1]), dtype=torch.float64, device="cuda") for _ in range(world)]
+    dist.all_gather(parts, torch.from_numpy(Ql).cuda())
+    out.update(mvproducts=int(hist.mvproducts), restarts=int(hist.restarts), nconverged=int(hist.nconverged),
+               converged=bool(hist.converged))
+    if rank == 0:
+        Q = torch.cat(parts).cpu().numpy()
+        out["residual_AQ_QR"] = float(np.linalg.norm(A @ Q - Q @ P.R))
+        out["residual_bound_n_tol"] = n * bench.TOL
+        out["orthogonality"] = float(np.linalg.norm(Q.T @ Q - np.eye(Q.shape[1])))
+        Po, ho = oracle.partialschur(A, v1=v1g, nev=bench.NEV, mindim=bench.MINDIM, maxdim=bench.MAXDIM,
+                                     which=bench.WHICH, tol=bench.TOL)
+        out["oracle_mvproducts"] = int(ho.mvproducts)
+        lam = np.sort_complex(P.eigenvalues)[-bench.NEV:]
+        lamo = np.sort_complex(Po.eigenvalues)[-bench.NEV:]
+        out["eig_relerr_max"] = float((np.abs(lam - lamo) / np.abs(lamo)).max())
+        out["oracle_seconds"] = round(time.time() - t0, 1)
+        print(json.dumps(out), flush=True)
+        assert hist.converged and ho.converged
+        assert abs(hist.mvproducts - ho.mvproducts) <= bench.MAXDIM - bench.MINDIM, out
+        assert out["eig_relerr_max"] <= 10 * bench.TOL, out
+        assert out["residual_AQ_QR"] <= n * bench.TOL and out["orthogonality"] < 1e-12, out
+    ws.close()
+    op.close()
+    dist.barrier()
+    if rank == 0:
+        print("DIST_GPU_BIG_OK", flush=True)
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = b2a.Context.from_torch_distributed(local)
+    if "--big" in sys.argv:
+        i = sys.argv.index("--big")
+        rows = int(float(sys.argv[i + 1])) if len(sys.argv) > i + 1 else 1_000_000
+        big(ctx, rank, world, rows)
+        dist.destroy_process_group()
+        return
 
     for T in (np.float64, np.complex128):
         rng = np.random.default_rng(5)

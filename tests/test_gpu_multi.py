@@ -11,17 +11,44 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("fused_sweep,port", [("1", "29517"), ("2", "29518"), ("0", "29519")],
-                         ids=["default", "fused_sweep_on_shards", "four_kernels"])
-def test_two_gpu_row_sharded_parity(fused_sweep, port):
-    """default: four-kernel chain with in-kernel collectives over NVLink peer memory; B2A_FUSED_SWEEP=2: the fused
-    orthogonalisation kernel with the all-reduces inside its grid barriers (both verified on 2 x B200)."""
+VARIANTS = {
+    # default: staged copy-engine exchange + owner-blocked mat-vec + fused orthogonalisation kernel
+    "default": {},
+    "staged_four_kernels": {"B2A_FUSED_SWEEP": "0"},
+    "staged_sm_copies": {"B2A_XCHG_SM": "16"},
+    "staged_without_owner_blocks": {"B2A_OWNER_BLOCKS": "0"},
+    # round-1 exchange: x pushed from inside the normalising kernel
+    "push_fused_sweep": {"B2A_XCHG": "0", "B2A_FUSED_SWEEP": "2"},
+    "push_four_kernels": {"B2A_XCHG": "0", "B2A_FUSED_SWEEP": "0"},
+    "nccl_collectives": {"B2A_NO_PEER": "1"},
+}
+
+
+def run_check(world, port, env_extra, args=()):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_gpu_check.py"), *args]
+    env = dict(os.environ, **env_extra)
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+
+
+@pytest.mark.parametrize("variant", sorted(VARIANTS))
+def test_two_gpu_row_sharded_parity(variant):
+    """H, Schur vectors, eigenvalues and breakdown handling of the row-sharded path against the oracle on the whole
+    matrix, for every exchange / orthogonalisation variant (tests/dist_gpu_check.py)."""
     import torch
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", port, os.path.join(ROOT, "tests", "dist_gpu_check.py")]
-    env = dict(os.environ, B2A_FUSED_SWEEP=fused_sweep)
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    res = run_check(2, 29517 + sorted(VARIANTS).index(variant), VARIANTS[variant])
     assert "DIST_GPU_CHECK_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_baseline_size_parity_on_all_gpus(world):
+    """bench.py's matrix at 1e6 rows per GPU on `world` GPUs against the oracle on the whole matrix."""
+    import torch
+
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs >= {world} GPUs")
+    res = run_check(world, 29540 + world, {}, ("--big", "1000000"))
+    assert "DIST_GPU_BIG_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]

@@ -64,3 +64,37 @@ def test_partialschur_is_bit_reproducible(ctx, T):
     assert out[0][0] == out[1][0] and out[0][1] == out[1][1]
     for a, b in zip(out[0][2:], out[1][2:]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("T", [np.float64, np.complex128])
+def test_fused_sweep_barrier_regions_many_ctas_one_tile(ctx, monkeypatch, T):
+    """Widest window of the round-1 write-after-read hazard on the per-CTA partial sums of the fused sweep: many CTAs,
+    ONE resident tile each, so phase P2 takes ~1 us and a fast CTA stores its barrier-B partials while a slow one is
+    still summing barrier A's.  Every barrier now owns its region (kernels_cgs_sweep.cuh kSweepPartRegion): the H
+    column must equal the oracle's AND be bit-identical over many repetitions."""
+    import oracle
+
+    monkeypatch.setenv("B2A_FUSED_SWEEP", "1")
+    rng = np.random.default_rng(17)
+    j = 24
+    n = 148 * (256 if T is np.float64 else 128)  # one TMA tile per CTA at this panel width
+    Vp = np.linalg.qr(rng.standard_normal((n, j)) + (1j * rng.standard_normal((n, j)) if T is np.complex128 else 0))[0]
+    x = (rng.standard_normal(n) + (1j * rng.standard_normal(n) if T is np.complex128 else 0)).astype(T)
+    x = x + Vp @ rng.standard_normal(j) * 100  # wnorm / rnorm ~ 0.4 < eta: DGKS fires, all three barriers run
+    ws = b2a.ArnoldiWorkspace(n, j + 1, dtype=T, ctx=ctx)
+    for c in range(j):
+        ws.set_col(c + 1, Vp[:, c].astype(T))
+    arn = oracle.ArnoldiWorkspace(T, n, j + 1)
+    arn.V[:, :j] = Vp
+    arn.V[:, j] = x
+    assert oracle.orthogonalize(arn, j) is True
+    first = None
+    for rep in range(300):
+        ws.set_col(j + 1, x)
+        assert ws.orthogonalize(j) is True
+        h = np.array(ws.H[: j + 1, j - 1]).copy()
+        if first is None:
+            first = h
+            assert np.abs(h - arn.H[: j + 1, j - 1]).max() <= 1e-12 * np.abs(arn.H[: j + 1, j - 1]).max()
+        assert np.array_equal(h, first), rep
+    ws.close()

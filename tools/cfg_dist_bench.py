@@ -130,25 +130,41 @@ def main():
                    ms=round(ms, 2), steps_per_s=round(hist.mvproducts / (ms * 1e-3), 1),
                    algorithmic_GBs_aggregate=round(gbs, 1), frac_of_aggregate_hbm_peak=round(gbs / (peak * world), 4),
                    collectives=ws.comm_mode, gen_s=round(t_gen, 1),
+                   env={k: v for k, v in os.environ.items() if k.startswith("B2A_")},
+                   nvlink_bytes_sent_per_step_per_gpu=(world - 1) * cnt * np.dtype(T).itemsize,
                    kernels_rank0={k: dict(launches=r["launches"], avg_us=round(1e3 * r["ms"] / r["launches"], 1),
                                           gbs=round(r["bytes"] / (r["ms"] * 1e-3) / 1e9))
                                   for k, r in prof.items() if r["launches"]})
 
     if args.residual and hist.nconverged:
+        # E = A Q - Q R on this rank's rows (one extra distributed mat-vec per Schur vector, x exchange included).
+        # Per eigenpair (lambda, y) of R with ||y|| = 1 the eigenvector is x = Q y and  A x - lambda x = E y  exactly,
+        # so ||A x - lambda x|| / |lambda| (the reference's convergence measure, src/run.jl:192-208) needs no further
+        # mat-vec: squared norms of the row blocks of E y are summed over the ranks.
         nc, spare = hist.nconverged, cfg["maxdim"] + 1
         Q = ws.get_cols(1, nc)  # local row block of the Schur vectors
         R = P.R
-        sq = 0.0
+        E = np.empty((cnt, nc), dtype=Q.dtype, order="F")
         for i in range(nc):
-            ws.matvec(op, i + 1, spare)  # A q_i on the device, x exchange included
-            aq = ws.get_cols(spare, 1)[:, 0]
-            sq += float(np.linalg.norm(aq - Q @ R[:, i]) ** 2)
-        t = torch.tensor([sq], dtype=torch.float64, device="cuda")
+            ws.matvec(op, i + 1, spare)
+            E[:, i] = ws.get_cols(spare, 1)[:, 0] - Q @ R[:, i]
+        lam, Y = np.linalg.eig(R)
+        Y = Y / np.linalg.norm(Y, axis=0)
+        EY = E @ Y
+        sq = np.concatenate([[np.linalg.norm(E) ** 2], np.sum(np.abs(EY) ** 2, axis=0),
+                             [np.linalg.norm(Q.conj().T @ Q) ** 2 if world == 1 else 0.0]])
+        t = torch.from_numpy(sq).cuda()
         if world > 1:
             dist.all_reduce(t)
+        t = t.cpu().numpy()
         if rank == 0:
-            out["residual_AQ_QR"] = float(np.sqrt(t.item()))
+            pair = np.sqrt(t[1 : 1 + nc]) / np.abs(lam)
+            out["residual_AQ_QR"] = float(np.sqrt(t[0]))
             out["residual_bound_n_tol"] = n * args.tol
+            out["eigenpair_residual_rel_max"] = float(pair.max())
+            out["eigenpair_residual_rel"] = [float(f"{v:.3e}") for v in pair]
+            out["eigenvalues_abs"] = [float(f"{abs(v):.6f}") for v in lam]
+            out["tol"] = args.tol
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -54,6 +54,8 @@ if __name__ == "__main__":
     if "--fp64-peak" in sys.argv:
         fp64 = float(sys.argv[sys.argv.index("--fp64-peak") + 1])
     rows = []
+    if "--only" in sys.argv:
+        SHAPES[:] = [SHAPES[int(sys.argv[sys.argv.index("--only") + 1])]]
     for name, T, n, maxdim, purge, k in SHAPES:
         K, N = maxdim - purge + 1, k - purge + 1
         flops = 2.0 * n * K * N * (4 if T is np.complex128 else 1)

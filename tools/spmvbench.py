@@ -37,12 +37,16 @@ def main():
     configs = [dict()]
     if "--blocksweep" in sys.argv:
         configs = [dict(B2A_SPMV_BLOCK_MB=str(mb)) for mb in (0, 16, 24, 32, 48, -1)]
+    if "--esweep" in sys.argv:  # entries in flight per lane x lanes per row x rows in flight
+        lprs = [int(v) for v in os.environ.get("SWEEP_LPR", "2,4,8").split(",")]
+        configs = [dict(B2A_SPMV_E=str(e), B2A_SPMV_LPR=str(l), B2A_SPMV_U=str(u))
+                   for e in (1, 2, 4) for l in lprs for u in (2, 4)]
     if "--sweep" in sys.argv:
         lprs = [int(v) for v in os.environ.get("SWEEP_LPR", "8,16").split(",")]
         configs = [dict(B2A_SPMV_U=str(u), B2A_SPMV_GRID=str(g), B2A_SPMV_LPR=str(l))
                    for l in lprs for u in (2, 4, 8) for g in (8, 16)]
     for cfg in configs:
-        for k_ in ("B2A_SPMV_U", "B2A_SPMV_GRID", "B2A_SPMV_LPR", "B2A_SPMV_BLOCK_MB"):
+        for k_ in ("B2A_SPMV_U", "B2A_SPMV_GRID", "B2A_SPMV_LPR", "B2A_SPMV_BLOCK_MB", "B2A_SPMV_E"):
             os.environ.pop(k_, None)
         os.environ.update(cfg)
         op = b2a.Operator.from_matrix(ctx, A)
