@@ -156,6 +156,10 @@ struct b2a_ctx {
   std::vector<cudaEvent_t> xchg_done;   // one per side stream: its last transfer + publication
   cudaEvent_t xchg_ready = nullptr;     // main stream: the column to exchange is final
   unsigned long long x_seq = 0;
+  // device table of consecutive exchange numbers: the per-slice flag is published by an 8-byte COPY-ENGINE transfer
+  // from this table (a kernel would need an SM slot, and the mat-vec launches that spin on the flags may hold them all)
+  unsigned long long *xchg_seq_table = nullptr;
+  unsigned long long xchg_table_base = 0;
   // kernels whose opt-in dynamic shared memory limit has been raised on THIS device (the attribute is per device
   // and per function; a process may drive several GPUs through several contexts)
   std::vector<const void *> smem_attr_done;
@@ -315,10 +319,8 @@ struct b2a_ws {
   int x_pushed_col = -1;  // 0-based column whose normalised content currently sits in every rank's x buffer
   // staged exchange (default on row-sharded workspaces that own the peer block; B2A_XCHG=0 selects the push from
   // inside the normalising kernel): copy-engine transfers on side streams, one flag per owner slice, the mat-vec
-  // runs owner block by owner block behind the arrivals.  xchg_sm = 1: SM copy kernels instead of copy engines.
+  // runs owner block by owner block behind the arrivals.
   bool xchg_staged = false;
-  int xchg_sm = 0;
-  unsigned int *xchg_ticket = nullptr;  // last-CTA counters of the SM copy kernels, one per side stream
   // rotation: Q travels host -> device through two alternating pinned slots (no stream synchronisation per
   // rotation: a slot is re-used only after the event behind its last copy)
   size_t q_bytes = 0, qpin_off = 0;
@@ -824,6 +826,42 @@ static cudaError_t launch_spmv_owner(b2a_op *A, const DT *x_local_shifted, const
   }
   return cudaSuccess;
 }
+// ... or all owner blocks in ONE launch (kernels_spmv.cuh spmv_owner_fused_kernel): row sums stay in registers across
+// the blocks.  Default; B2A_OWNER_FUSED=0 selects one launch per block.  Returns cudaErrorNotSupported when the lane
+// configuration has no instantiation (very dense rows) - the caller then takes the per-block launches.
+static bool g_owner_fused = !(getenv("B2A_OWNER_FUSED") && getenv("B2A_OWNER_FUSED")[0] == '0');
+template <class DT, int LPR, int E>
+static cudaError_t launch_spmv_owner_fused_inst(b2a_op *A, const DT *x_own, const DT *x_buf, DT *y, const int *poison,
+                                                cudaStream_t st, const XWait &xw) {
+  constexpr int U = 4;
+  const int64_t threads = cdiv(A->n_local, U) * LPR;
+  const int64_t grid = std::max<int64_t>(1, cdiv(threads, 256));  // every lane group owns <= U rows: no grid stride
+  if (grid > 2147483647LL) return cudaErrorNotSupported;
+  return launch_pdl(b2a::spmv_owner_fused_kernel<DT, LPR, U, E>, (unsigned)grid, 256u, 0, st, A->n_local,
+                    (const int64_t *)A->d_ptr, (const int32_t *)A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x_own,
+                    x_buf, y, poison, xw);
+}
+template <class DT, int LPR>
+static cudaError_t launch_spmv_owner_fused_e(b2a_op *A, const DT *x_own, const DT *x_buf, DT *y, const int *poison,
+                                             cudaStream_t st, const XWait &xw) {
+  // entries per lane of one (row, owner block) segment
+  const double per_lane = (double)A->nnz / std::max<double>(1.0, (double)A->n_local * A->nblocks) / LPR;
+  if (per_lane >= 3.0) return launch_spmv_owner_fused_inst<DT, LPR, 4>(A, x_own, x_buf, y, poison, st, xw);
+  if (per_lane >= 1.5) return launch_spmv_owner_fused_inst<DT, LPR, 2>(A, x_own, x_buf, y, poison, st, xw);
+  return launch_spmv_owner_fused_inst<DT, LPR, 1>(A, x_own, x_buf, y, poison, st, xw);
+}
+template <class DT>
+static cudaError_t launch_spmv_owner_fused(b2a_op *A, const DT *x_own, const DT *x_buf, DT *y, const int *poison,
+                                           cudaStream_t st, const XWait &xw) {
+  switch (A->lpr) {
+    case 1:
+    case 2: return launch_spmv_owner_fused_e<DT, 2>(A, x_own, x_buf, y, poison, st, xw);
+    case 4: return launch_spmv_owner_fused_e<DT, 4>(A, x_own, x_buf, y, poison, st, xw);
+    case 8: return launch_spmv_owner_fused_e<DT, 8>(A, x_own, x_buf, y, poison, st, xw);
+    default: return cudaErrorNotSupported;
+  }
+}
+
 template <class DT, int LPR>
 static cudaError_t launch_spmv_vec(b2a_op *A, const DT *x, DT *y, const int *poison, cudaStream_t st, int sms,
                                    const XWait &xw) {
@@ -876,9 +914,11 @@ template <class DT> static int launch_spmv_tma(b2a_op *A, const DT *x, DT *y, co
 // Row-sharded mat-vec input (SURVEY 8(e) "x-exchange"): rank s owns rows [off_s, off_s + cnt_s) of the new basis
 // vector and every rank needs (in general) all of it.  Stage k = 1 .. P-1 sends this rank's slice to rank
 // (rank - k) mod P - a permutation per stage, so every NVLink port carries one slice in and one out at a time -
-// as ONE copy-engine transfer (no SM store-issue limit, no SMs taken from the mat-vec) followed by a one-thread
-// kernel that publishes the exchange number in the receiver's flag for this sender (st.release.sys; stream order
-// puts it behind the copy).  The receiver runs its mat-vec owner block by owner block in the same order
+// as ONE copy-engine transfer (no SM store-issue limit, no SMs taken from the mat-vec) followed by an 8-byte
+// copy-engine transfer that publishes the exchange number in the receiver's flag for this sender (stream order
+// puts it behind the data).  No kernel is involved on the sending side: the mat-vec launches that spin on the
+// flags can occupy every SM slot of a GPU, and a flag-publishing kernel queued behind them would never start
+// while its peer waits for that very flag.  The receiver runs its mat-vec owner block by owner block in the same order
 // (own block, rank+1, rank+2, ...): the gathers on the blocks that have arrived hide the transfer of the others.
 // Two x buffers (exchange-number parity): a rank that is one mat-vec ahead never overwrites what a peer still reads.
 static int xchg_ensure_streams(b2a_ctx *ctx, int want) {
@@ -896,6 +936,21 @@ static int xchg_ensure_streams(b2a_ctx *ctx, int want) {
   return B2A_OK;
 }
 
+constexpr unsigned long long kXchgTableSize = 1ull << 16;
+// (Re)fill the table so that it covers exchange number `seq`; a refill (every 65536 exchanges) drains the streams.
+static int xchg_ensure_table(b2a_ctx *ctx, unsigned long long seq) {
+  if (ctx->xchg_seq_table && seq >= ctx->xchg_table_base && seq - ctx->xchg_table_base < kXchgTableSize) return B2A_OK;
+  if (!ctx->xchg_seq_table)
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&ctx->xchg_seq_table), kXchgTableSize * sizeof(unsigned long long)));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  for (auto st : ctx->xchg_streams) CUDA_TRY(cudaStreamSynchronize(st));
+  std::vector<unsigned long long> host(kXchgTableSize);
+  for (unsigned long long i = 0; i < kXchgTableSize; ++i) host[i] = seq + i;
+  CUDA_TRY(cudaMemcpy(ctx->xchg_seq_table, host.data(), kXchgTableSize * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+  ctx->xchg_table_base = seq;
+  return B2A_OK;
+}
+
 static int g_xchg_nstreams = getenv("B2A_XCHG_STREAMS") ? std::max(1, atoi(getenv("B2A_XCHG_STREAMS"))) : 3;
 
 // Enqueue the exchange of workspace column jsrc0; returns the exchange number the consumers wait for.
@@ -906,6 +961,8 @@ template <class DT> static int enqueue_xchg(b2a_ws *ws, const DT *xl, unsigned l
   const int ns = std::min(g_xchg_nstreams, P - 1);
   B2A_TRY(xchg_ensure_streams(ctx, ns));
   const unsigned long long seq = ++ctx->x_seq;
+  B2A_TRY(xchg_ensure_table(ctx, seq));
+  const unsigned long long *seq_src = ctx->xchg_seq_table + (seq - ctx->xchg_table_base);
   const size_t bytes = (size_t)ws->n_local * sizeof(DT);
   const size_t xoff = pv.off_x + (seq & 1ull) * pv.x_stride + (size_t)ws->row_offset * sizeof(DT);
   CUDA_TRY(cudaEventRecord(ctx->xchg_ready, ctx->stream));
@@ -917,18 +974,9 @@ template <class DT> static int enqueue_xchg(b2a_ws *ws, const DT *xl, unsigned l
     const int dst = (me - k + P) % P;
     cudaStream_t st = ctx->xchg_streams[(k - 1) % ns];
     unsigned long long *flag = reinterpret_cast<unsigned long long *>(pv.peer[dst] + pv.off_flag_xs) + me;
-    if (ws->xchg_sm) {
-      const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(ws->xchg_sm, cdiv((int64_t)bytes, 256 * 16 * 4)));
-      b2a::xsend_kernel<<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const double *>(xl),
-                                                        reinterpret_cast<double *>(pv.peer[dst] + xoff),
-                                                        (int64_t)(bytes / 8), flag, seq,
-                                                        ws->xchg_ticket + ((k - 1) % ns));
-    } else {
-      if (bytes) CUDA_TRY(cudaMemcpyAsync(pv.peer[dst] + xoff, xl, bytes, cudaMemcpyDeviceToDevice, st));
-      b2a::xflag_kernel<<<1, 32, 0, st>>>(flag, seq);
-    }
-    ctx->launches++;
-    CUDA_TRY(cudaGetLastError());
+    // slice, then its flag: both copy-engine transfers, ordered by the stream
+    if (bytes) CUDA_TRY(cudaMemcpyAsync(pv.peer[dst] + xoff, xl, bytes, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(flag, seq_src, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
   }
   for (int i = 0; i < ns; ++i) CUDA_TRY(cudaEventRecord(ctx->xchg_done[i], ctx->xchg_streams[i]));
   if (ctx->prof_on) {  // e1 of the exchange record: after the last operation of the first side stream
@@ -965,7 +1013,7 @@ template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, 
     xw.pv = ws->peer;
     xw.want = seq;
     x = xbuf;
-    if (A->owner_blocks && A->kind == OP_CSR) {
+    if (A->owner_blocks && A->kind == OP_CSR && ws->uniform_partition && ws->all_counts[0] == A->owner_W) {
       owner_passes = true;
     } else {
       // operator not stored by owner block: own slice into the buffer (stream-ordered), then wait for all the others
@@ -1020,7 +1068,13 @@ template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, 
     }
   } else if (owner_passes) {
     const DT *xls = xl - ws->row_offset;  // global column c of the own block -> workspace row c - row_offset
-    switch (A->lpr) {
+    le = cudaErrorNotSupported;
+    if (g_owner_fused) {
+      XWait w = xw;
+      w.mode = 2;
+      le = launch_spmv_owner_fused<DT>(A, xls, x, y, poison, ctx->stream, w);
+    }
+    if (le == cudaErrorNotSupported) switch (A->lpr) {
       case 1:
       case 2: le = launch_spmv_owner<DT, 2>(A, xls, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches); break;
       case 4: le = launch_spmv_owner<DT, 4>(A, xls, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches); break;
@@ -1132,9 +1186,9 @@ struct RotPlan {
 };
 // Largest row tile (16 rows per consumer warp) that leaves at least two ring stages, Q fragments in shared memory
 // when they fit beside them.
-static bool rot_plan(const b2a_ws *ws, int K, int N, bool cplx, RotPlan *p) {
+static bool rot_plan(const b2a_ws *ws, int K, int N, bool cplx, RotPlan *p, bool cplx_out = false) {
   const int inner = cplx ? 2 : 1, parts = cplx ? 2 : 1;
-  const int ntiles_n = (N * inner + 7) / 8;  // 8-wide output tiles of the real view
+  const int ntiles_n = (N * ((cplx || cplx_out) ? 2 : 1) + 7) / 8;  // 8-wide output tiles of the real view
   int best_nt = 4, best_pad = 1 << 30;
   for (int nt = 4; nt >= 1; --nt) {
     const int pad = (int)cdiv(ntiles_n, nt) * nt;
@@ -1229,22 +1283,34 @@ template <> void pack_b_fragments<cplx>(const cplx *Qp, int K, int N, const RotP
       }
 }
 
-template <bool CPLX, int NT, int MINB>
+// out == nullptr: in place (the rotation); else the product goes to out[:, 0 : N) with leading dimension ldo
+template <bool CPLX, bool CPLX_OUT, int NT, int MINB>
 static int launch_rotate_mma_inst2(b2a_ws *ws, const CUtensorMap &tm, int col0, int N, const RotPlan &p, int move_src,
-                                   int move_dst) {
-  auto kern = b2a::rotate_mma_kernel<CPLX, NT, MINB>;
+                                   int move_dst, double *out, int64_t ldo) {
+  auto kern = b2a::rotate_mma_kernel<CPLX, CPLX_OUT, NT, MINB>;
   B2A_TRY(ensure_smem_attr(ws->ctx, kern, kTmaSmemBudget / MINB));
+  double *V = reinterpret_cast<double *>(ws->dV);
   kern<<<(unsigned)p.grid, b2a::kRotThreads, p.smem, ws->ctx->stream>>>(
-      tm, reinterpret_cast<double *>(ws->dV), ws->ld, col0, N, reinterpret_cast<const double *>(ws->dQ), p.KS, p.NCH,
-      p.g, move_src, move_dst, p.b_in_smem);
+      tm, V, ws->ld, out ? out : V, out ? ldo : ws->ld, out ? 0 : col0, N, reinterpret_cast<const double *>(ws->dQ),
+      p.KS, p.NCH, p.g, move_src, move_dst, p.b_in_smem);
   CUDA_TRY(cudaGetLastError());
   return B2A_OK;
 }
-template <bool CPLX, int NT>
+template <bool CPLX, bool CPLX_OUT, int NT>
 static int launch_rotate_mma_inst(b2a_ws *ws, const CUtensorMap &tm, int col0, int N, const RotPlan &p, int move_src,
-                                  int move_dst) {
-  if (p.ctas > 1) return launch_rotate_mma_inst2<CPLX, NT, 2>(ws, tm, col0, N, p, move_src, move_dst);
-  return launch_rotate_mma_inst2<CPLX, NT, 1>(ws, tm, col0, N, p, move_src, move_dst);
+                                  int move_dst, double *out = nullptr, int64_t ldo = 0) {
+  if (p.ctas > 1) return launch_rotate_mma_inst2<CPLX, CPLX_OUT, NT, 2>(ws, tm, col0, N, p, move_src, move_dst, out, ldo);
+  return launch_rotate_mma_inst2<CPLX, CPLX_OUT, NT, 1>(ws, tm, col0, N, p, move_src, move_dst, out, ldo);
+}
+template <bool CPLX, bool CPLX_OUT>
+static int launch_rotate_mma_nt(b2a_ws *ws, const CUtensorMap &tm, int col0, int N, const RotPlan &p, int move_src,
+                                int move_dst, double *out = nullptr, int64_t ldo = 0) {
+  switch (p.NT) {
+    case 1: return launch_rotate_mma_inst<CPLX, CPLX_OUT, 1>(ws, tm, col0, N, p, move_src, move_dst, out, ldo);
+    case 2: return launch_rotate_mma_inst<CPLX, CPLX_OUT, 2>(ws, tm, col0, N, p, move_src, move_dst, out, ldo);
+    case 3: return launch_rotate_mma_inst<CPLX, CPLX_OUT, 3>(ws, tm, col0, N, p, move_src, move_dst, out, ldo);
+    default: return launch_rotate_mma_inst<CPLX, CPLX_OUT, 4>(ws, tm, col0, N, p, move_src, move_dst, out, ldo);
+  }
 }
 
 // host -> device copy of a small array through one of the two pinned Q slots, no stream synchronisation
@@ -1277,14 +1343,40 @@ static int rotate_mma(b2a_ws *ws, int col0, int K, int N, const HT *Qp, int move
   pack_b_fragments<HT>(Qp, K, N, p, slot);
   B2A_TRY(stage_q_send(ws, slot, p.b_elems * 8));
   prof_begin(ws->ctx, B2A_K_ROTATE, (double)ws->n_local * sizeof(DT) * (K + N + (move_dst >= 0 ? 2.0 : 0.0)));
-  int s;
-  switch (p.NT) {
-    case 1: s = launch_rotate_mma_inst<CPLX, 1>(ws, tm, col0, N, p, move_src, move_dst); break;
-    case 2: s = launch_rotate_mma_inst<CPLX, 2>(ws, tm, col0, N, p, move_src, move_dst); break;
-    case 3: s = launch_rotate_mma_inst<CPLX, 3>(ws, tm, col0, N, p, move_src, move_dst); break;
-    default: s = launch_rotate_mma_inst<CPLX, 4>(ws, tm, col0, N, p, move_src, move_dst); break;
-  }
+  const int s = launch_rotate_mma_nt<CPLX, CPLX>(ws, tm, col0, N, p, move_src, move_dst);
   prof_end(ws->ctx);
+  ws->ctx->launches++;
+  return s;
+}
+
+// X[:, 0 : N) = V[:, 0 : K) * Y with a COMPLEX K x N coefficient matrix Y (packed, column-major, host) into the
+// device buffer dX (complex, leading dimension ldx >= ws->ld rows: whole tiles are written) - partialeigen's Q * Y
+// (src/eigvals.jl:94) on the same TMA + DMMA kernel.  Returns 1 when the shape cannot be planned.
+template <class HT> static int basis_times_mma(b2a_ws *ws, int K, int N, const cplx *Yp, cdouble *dX, int64_t ldx) {
+  using DT = typename Dev<HT>::type;
+  constexpr bool CPLX = b2a::Scalar<DT>::is_complex;
+  if (!ws->rotate_mode || !ws->use_tma || get_encode_tiled() == nullptr) return 1;
+  RotPlan p;
+  if (!rot_plan(ws, K, N, CPLX, &p, true)) return 1;
+  CUtensorMap tm;
+  if (!make_rot_tmap(ws, 0, K, p.g, &tm)) return 1;
+  double *slot = nullptr;
+  if (p.b_elems * 8 > ws->q_bytes) return 1;
+  B2A_TRY(stage_q(ws, p.b_elems * 8, &slot));
+  if (CPLX) {
+    pack_b_fragments<cplx>(Yp, K, N, p, slot);
+  } else {
+    // real basis: B = Y as interleaved (re, im) real columns, K x 2N
+    std::vector<double> Yr((size_t)K * 2 * N);
+    for (int o = 0; o < N; ++o)
+      for (int c = 0; c < K; ++c) {
+        Yr[(size_t)(2 * o) * K + c] = Yp[(size_t)o * K + c].real();
+        Yr[(size_t)(2 * o + 1) * K + c] = Yp[(size_t)o * K + c].imag();
+      }
+    pack_b_fragments<double>(Yr.data(), K, 2 * N, p, slot);
+  }
+  B2A_TRY(stage_q_send(ws, slot, p.b_elems * 8));
+  const int s = launch_rotate_mma_nt<CPLX, true>(ws, tm, 0, N, p, -1, -1, reinterpret_cast<double *>(dX), ldx);
   ws->ctx->launches++;
   return s;
 }
@@ -1633,6 +1725,7 @@ int b2a_ctx_destroy(b2a_ctx *ctx) {
   for (auto st : ctx->xchg_streams) cudaStreamDestroy(st);
   for (auto e : ctx->xchg_done) cudaEventDestroy(e);
   if (ctx->xchg_ready) cudaEventDestroy(ctx->xchg_ready);
+  if (ctx->xchg_seq_table) cudaFree(ctx->xchg_seq_table);
   if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
   if (ctx->d_zero) cudaFree(ctx->d_zero);
   for (auto &pc : ctx->pinned_cache) cudaFreeHost(pc.second);
@@ -1727,12 +1820,15 @@ static int upload_index(b2a_ctx *ctx, const void *host, int64_t count, int idx_w
   return B2A_OK;
 }
 
+static int pick_entries_in_flight(int64_t nnz, int64_t nrows, int lpr);
 static void op_tuning(b2a_op *op) {
   if (const char *e = getenv("B2A_SPMV_U")) op->rows_in_flight = atoi(e);
   if (const char *e = getenv("B2A_SPMV_GRID")) op->grid_mult = std::max(1, atoi(e));
-  if (const char *e = getenv("B2A_SPMV_E")) op->entries_in_flight = atoi(e);
+
   if (const char *e = getenv("B2A_SPMV_LPR")) op->lpr = atoi(e);
   if (const char *e = getenv("B2A_SPMV_STAGES")) op->tma_stages = atoi(e);
+  op->entries_in_flight = pick_entries_in_flight(op->nnz, op->n_local, op->lpr);
+  if (const char *e = getenv("B2A_SPMV_E")) op->entries_in_flight = atoi(e);
 }
 
 extern "C++" {
@@ -1780,6 +1876,18 @@ static int pick_lanes(int64_t nnz, int64_t nrows) {
   int lpr = 2;
   while (lpr < 32 && lpr * 2 <= avg / 4.0) lpr *= 2;
   return lpr;
+}
+
+// Entries per lane and row issued together (template parameter E of the vector kernel): the largest power of two
+// <= (entries per row) / LPR, at most 4.  Measured on B200 (tools/spmvbench.py --esweep, profiles/r2_spmv_esweep_*):
+// 16 random entries per row, LPR 4: E = 4 88.6 us vs E = 1 93.2; 7-point Laplacian 160^3, LPR 2: E = 2 85.5 us
+// (5.15 TB/s) vs E = 1 91.4 and E = 4 95.1 (masked slots cost registers); ComplexF64 20 per row, LPR 4: E = 4
+// 238 us vs E = 1 279.
+static int pick_entries_in_flight(int64_t nnz, int64_t nrows, int lpr) {
+  const double per_lane = nrows > 0 ? (double)nnz / (double)nrows / (double)std::max(lpr, 1) : 0.0;
+  int e = 1;
+  while (e < 4 && e * 2 <= per_lane) e *= 2;
+  return e;
 }
 
 static int op_alloc(b2a_ctx *ctx, b2a_op *op, int64_t nptr) {
@@ -2295,6 +2403,7 @@ static int peer_setup(b2a_ctx *ctx, b2a_ws *ws) {
   const size_t o_flag_x = carve(sizeof(unsigned long long) * P);
   const size_t o_flag_xs = carve(sizeof(unsigned long long) * P);
   const size_t o_data = carve(sizeof(double) * b2a::kPeerBufs * P * slot);
+  const size_t o_ll = carve((size_t)16 * b2a::kPeerBufs * P * slot);
   const size_t o_x = carve(2 * x_bytes);  // two buffers: exchange-number parity (staged exchange)
   const size_t total = off;
   int okflag = 1;
@@ -2374,6 +2483,8 @@ static int peer_setup(b2a_ctx *ctx, b2a_ws *ws) {
   pv.off_flag_xs = o_flag_xs;
   pv.off_x = o_x;
   pv.x_stride = x_bytes;
+  pv.off_ll = o_ll;
+  pv.ll = !(getenv("B2A_AR_LL") && getenv("B2A_AR_LL")[0] == '0');
   pv.seq_ar = reinterpret_cast<unsigned long long *>(ctx->peer_local + o_hdr);
   pv.seq_x = pv.seq_ar + 1;
   pv.err = reinterpret_cast<int *>(pv.seq_ar + 2);
@@ -2474,12 +2585,12 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
   // Q of a rotation: packed K x N for the DFMA kernels, MMA B-fragment order (padded) for the DMMA kernel
   {
     const size_t inner = es / 8, parts = inner;
-    const size_t frag = (size_t)((maxdim + 3) / 4) * ((inner * maxdim + 7) / 8 + 3) * parts * 32;
+    // n tiles of the real view: 2 (maxdim + 1) outputs cover a complex product of a real basis too (partialeigen)
+    const size_t frag = (size_t)((maxdim + 4) / 4) * ((2 * (maxdim + 1) + 7) / 8 + 3) * parts * 32;
     ws->q_bytes = (std::max<size_t>(frag, (size_t)maxdim * maxdim * inner) * 8 + 255) / 256 * 256;
   }
   const size_t o_dQ = carve(ws->q_bytes);
   const size_t o_flag = carve(sizeof(unsigned long long));
-  const size_t o_xt = carve(sizeof(unsigned int) * 32);
   const bool want_trace = getenv("B2A_SWEEP_TRACE") && getenv("B2A_SWEEP_TRACE")[0] == '1';
   const size_t o_trace = carve(want_trace ? sizeof(unsigned long long) * b2a::kSweepTraceSlots * ctx->num_sms : 8);
   CUDA_TRY(dev_alloc(ctx, &ws->arena, off));
@@ -2495,7 +2606,6 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
   ws->state = reinterpret_cast<b2a::SweepState *>(base + o_state);
   ws->dQ = base + o_dQ;
   ws->sweep_flag = reinterpret_cast<unsigned long long *>(base + o_flag);
-  ws->xchg_ticket = reinterpret_cast<unsigned int *>(base + o_xt);
   ws->sweep_trace = want_trace ? reinterpret_cast<unsigned long long *>(base + o_trace) : nullptr;
   ws->qpin_off = ((size_t)m1 * maxdim * es + sizeof(int) * (m1 + 1) + sizeof(b2a::SweepState) + 64 + 255) / 256 * 256;
   const size_t want = ws->qpin_off + 2 * ws->q_bytes;
@@ -2506,7 +2616,6 @@ static int ws_create_impl(b2a_ctx *ctx, int dtype, int64_t n_local, int64_t n_gl
   B2A_TRY(peer_setup(ctx, ws));
   // staged exchange: default whenever the peer block is available (B2A_XCHG=0: push from the normalising kernel)
   ws->xchg_staged = ws->peer.P > 1 && ws->peer_x && !(getenv("B2A_XCHG") && getenv("B2A_XCHG")[0] == '0');
-  if (const char *e = getenv("B2A_XCHG_SM")) ws->xchg_sm = std::max(0, atoi(e));
   if (ctx->world > 1 && (ws->peer.P == 1 || !ws->peer_x)) {  // NCCL all-gather needs its own gather buffer
     const int64_t nx = ws->uniform_partition ? ws->all_counts[0] * ctx->world : n_global;
     CUDA_TRY(dev_alloc(ctx, &ws->xfull, (size_t)nx * es));
@@ -2728,6 +2837,24 @@ int b2a_basis_times(b2a_ws *ws, int nconv, const double *Y, int ldy, double *X, 
     for (int c = 0; c < nconv; ++c) Yp[(size_t)o * nconv + c] = cplx(Y[2 * ((size_t)o * ldy + c)], Y[2 * ((size_t)o * ldy + c) + 1]);
   cdouble *dY = nullptr, *dX = nullptr;
   const int64_t n = ws->n_local;
+  // TMA + DMMA kernel (whole tiles are written: the device buffer has the workspace's padded leading dimension)
+  {
+    cudaError_t e = dev_alloc(ctx, reinterpret_cast<void **>(&dX), sizeof(cdouble) * (size_t)ws->ld * nconv);
+    CUDA_TRY(e);
+    const int s = ws->dtype == B2A_F64 ? eng::basis_times_mma<double>(ws, nconv, nconv, Yp.data(), dX, ws->ld)
+                                       : eng::basis_times_mma<cplx>(ws, nconv, nconv, Yp.data(), dX, ws->ld);
+    if (s == B2A_OK) {
+      e = cudaMemcpy2DAsync(X, (size_t)ldx * 16, dX, (size_t)ws->ld * 16, (size_t)n * 16, nconv, cudaMemcpyDeviceToHost,
+                            ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+      dev_free(ctx, dX);
+      CUDA_TRY(e);
+      return B2A_OK;
+    }
+    dev_free(ctx, dX);
+    dX = nullptr;
+    if (s != 1) return s;
+  }
   CUDA_TRY(dev_alloc(ctx, reinterpret_cast<void **>(&dY), sizeof(cdouble) * nconv * nconv));
   cudaError_t e = dev_alloc(ctx, reinterpret_cast<void **>(&dX), sizeof(cdouble) * (size_t)std::max<int64_t>(n, 1) * nconv);
   if (e != cudaSuccess) {

@@ -366,56 +366,4 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// ---- staged x exchange (b2a.cu enqueue_xchg) ---------------------------------------------------------------
-// xflag: one thread publishes the exchange number in the receiver's per-sender flag.  It runs on the side stream
-// right behind the copy-engine transfer of the slice, so stream order puts the flag behind the data.
-__global__ void xflag_kernel(unsigned long long *flag, unsigned long long seq) {
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    st_release_sys(flag, seq);
-  }
-}
-
-// xsend: the same stage with SM stores instead of a copy engine (B2A_XCHG_SM=<CTAs>): a few CTAs stream the slice
-// into the receiver's x buffer with 16-byte stores, the CTA that finishes last publishes the flag.
-__global__ void __launch_bounds__(256)
-    xsend_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t n, unsigned long long *flag,
-                 unsigned long long seq, unsigned int *ticket) {
-  const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  if (vec) {
-    const int64_t n2 = n >> 1;
-    const double2 *s2 = reinterpret_cast<const double2 *>(src);
-    double2 *d2 = reinterpret_cast<double2 *>(dst);
-    constexpr int U = 4;
-    for (int64_t i0 = tid; i0 < n2; i0 += stride * U) {
-      double2 x[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t i = i0 + u * stride;
-        if (i < n2) x[u] = s2[i];
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t i = i0 + u * stride;
-        if (i < n2) d2[i] = x[u];
-      }
-    }
-    if ((n & 1) && tid == 0) dst[n - 1] = src[n - 1];
-  } else {
-    for (int64_t i = tid; i < n; i += stride) dst[i] = src[i];
-  }
-  __shared__ int last_cta;
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) last_cta = (atomicAdd(ticket, 1u) == gridDim.x - 1u);
-  __syncthreads();
-  if (last_cta && threadIdx.x == 0) {
-    *ticket = 0u;
-    __threadfence_system();
-    st_release_sys(flag, seq);
-  }
-}
-
 }  // namespace b2a

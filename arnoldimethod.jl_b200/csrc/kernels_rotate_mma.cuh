@@ -52,11 +52,17 @@ __device__ __forceinline__ void dmma884(double (&d)[2], double a, double b) {
 }
 
 // V is addressed in doubles: element (row, col, part) of the workspace at (col * ld + row) * inner + part.
-template <bool CPLX, int NT, int MINB>
+// The product is written to Out[:, col0 : col0 + N) with leading dimension ldo (in elements of the OUTPUT type);
+// the rotation passes Out = V, ldo = ld (in place).  CPLX_OUT with a real input (CPLX = false) is the product of a
+// real basis with a complex coefficient matrix (partialeigen, src/eigvals.jl:94: X = Q * Y): B then holds Y as
+// interleaved (re, im) columns and an accumulator pair is one complex output element, exactly as in the
+// all-complex case.
+template <bool CPLX, bool CPLX_OUT, int NT, int MINB>
 __global__ void __launch_bounds__(kRotThreads, MINB)
-    rotate_mma_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ V, int64_t ld, int col0, int N,
-                      const double *__restrict__ Bg, int KS, int NCH, RotGeom g, int move_src, int move_dst,
-                      int b_in_smem) {
+    rotate_mma_kernel(const __grid_constant__ CUtensorMap tmap, double *__restrict__ V, int64_t ld,
+                      double *__restrict__ Out, int64_t ldo, int col0, int N, const double *__restrict__ Bg, int KS,
+                      int NCH, RotGeom g, int move_src, int move_dst, int b_in_smem) {
+  static_assert(CPLX_OUT || !CPLX, "a complex input has a complex output");
   extern __shared__ __align__(128) unsigned char rot_smem_raw[];
   constexpr int INNER = CPLX ? 2 : 1;
   constexpr int PARTS = CPLX ? 2 : 1;
@@ -174,16 +180,16 @@ __global__ void __launch_bounds__(kRotThreads, MINB)
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const int n0 = (ch * NT + nt) * 8 + 2 * tq;
-        if (!CPLX) {
+        if (!CPLX_OUT) {
 #pragma unroll
           for (int i = 0; i < 2; ++i)
             if (n0 + i < N)
-              *reinterpret_cast<double2 *>(V + (int64_t)(col0 + n0 + i) * ld + row0 + rw) =
+              *reinterpret_cast<double2 *>(Out + (int64_t)(col0 + n0 + i) * ldo + row0 + rw) =
                   make_double2(acc[0][nt][i], acc[1][nt][i]);
         } else {
           const int o = n0 >> 1;  // complex output column: the accumulator pair is (re, im)
           if (o < N) {
-            double2 *out = reinterpret_cast<double2 *>(V) + (int64_t)(col0 + o) * ld + row0 + rw;
+            double2 *out = reinterpret_cast<double2 *>(Out) + (int64_t)(col0 + o) * ldo + row0 + rw;
             out[0] = make_double2(acc[0][nt][0], acc[0][nt][1]);
             out[1] = make_double2(acc[1][nt][0], acc[1][nt][1]);
           }

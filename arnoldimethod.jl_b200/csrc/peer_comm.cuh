@@ -34,6 +34,9 @@ struct PeerView {
   // staged exchange (copy engines / per-owner flags): its own flag array, and a second x buffer (exchange number
   // parity selects the buffer, so a rank that runs one mat-vec ahead never overwrites what a peer still reads)
   unsigned long long off_flag_xs = 0, x_stride = 0;
+  // low-latency all-reduce cells (16 bytes per double: lo | flag | hi | flag), see peer_allreduce_ll_warp
+  unsigned long long off_ll = 0;
+  int ll = 0;
   unsigned long long *seq_ar = nullptr;  // local device counters
   unsigned long long *seq_x = nullptr;
   int *err = nullptr;
@@ -53,9 +56,62 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double *p) {
   return v;
 }
 
+// Low-latency variant (the default): every double travels as ONE 16-byte store {lo32, flag, hi32, flag} with
+// flag = the collective's sequence number, the way NCCL's LL protocol packs data and flag into 8-byte units that the
+// fabric delivers atomically.  The receiver polls the cell itself until both flags match: no __threadfence_system, no
+// separate flag round trip - one NVLink store latency per all-reduce instead of three dependent hops.  Cells of
+// buffer `seq % kPeerBufs` are rewritten four collectives later, by which time every reader has long passed (a rank
+// can only start collective s + 1 after all ranks have contributed to s).  Sum in rank order: identical bits everywhere.
+__device__ __forceinline__ void st_ll(uint4 *p, double v, unsigned flag) {
+  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(flag), "r"(hi), "r"(flag) : "memory");
+}
+__device__ __forceinline__ bool ld_ll(const uint4 *p, unsigned flag, double *v) {
+  unsigned lo, f1, hi, f2;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(p) : "memory");
+  *v = __hiloint2double((int)hi, (int)lo);
+  return f1 == flag && f2 == flag;
+}
+__device__ __forceinline__ void peer_allreduce_ll_warp(const PeerView &pv, double *vals, int cnt) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long seq = 0;
+  if (lane == 0) seq = atomicAdd(pv.seq_ar, 1ull) + 1ull;
+  seq = __shfl_sync(0xffffffffu, seq, 0);
+  const int buf = (int)(seq % kPeerBufs);
+  const unsigned flag = (unsigned)seq;
+  for (int i = lane; i < cnt; i += 32) {
+    const double v = vals[i];
+    for (int p = 0; p < pv.P; ++p) {
+      uint4 *dst = reinterpret_cast<uint4 *>(pv.peer[p] + pv.off_ll) + ((size_t)buf * pv.P + pv.rank) * pv.slot;
+      st_ll(dst + i, v, flag);
+    }
+  }
+  const uint4 *my = reinterpret_cast<const uint4 *>(pv.peer[pv.rank] + pv.off_ll) + (size_t)buf * pv.P * pv.slot;
+  for (int i = lane; i < cnt; i += 32) {
+    double s = 0.0;
+    for (int p = 0; p < pv.P; ++p) {
+      double v;
+      unsigned long long spins = 0;
+      while (!ld_ll(my + (size_t)p * pv.slot + i, flag, &v)) {
+        if (++spins > kPeerSpinLimit) {
+          *pv.err = 4;
+          break;
+        }
+      }
+      s += v;
+    }
+    vals[i] = s;
+  }
+  __syncwarp();
+}
+
 // In-place all-reduce (sum) of vals[0..cnt) across the P ranks.  Call with ONE full warp; vals is
 // local global memory already visible to the calling warp.
 __device__ __forceinline__ void peer_allreduce_warp(const PeerView &pv, double *vals, int cnt) {
+  if (pv.ll) {
+    peer_allreduce_ll_warp(pv, vals, cnt);
+    return;
+  }
   const int lane = threadIdx.x & 31;
   unsigned long long seq = 0;
   if (lane == 0) {

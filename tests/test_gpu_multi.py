@@ -15,7 +15,7 @@ VARIANTS = {
     # default: staged copy-engine exchange + owner-blocked mat-vec + fused orthogonalisation kernel
     "default": {},
     "staged_four_kernels": {"B2A_FUSED_SWEEP": "0"},
-    "staged_sm_copies": {"B2A_XCHG_SM": "16"},
+    "staged_one_side_stream": {"B2A_XCHG_STREAMS": "1"},
     "staged_without_owner_blocks": {"B2A_OWNER_BLOCKS": "0"},
     # round-1 exchange: x pushed from inside the normalising kernel
     "push_fused_sweep": {"B2A_XCHG": "0", "B2A_FUSED_SWEEP": "2"},

@@ -427,3 +427,71 @@ def test_matrix_free_operator_end_to_end():
     Po, ho = oracle.partialschur(Ad.tocsr(), v1=v1, nev=6, which="LM", tol=1e-8)
     assert hist.mvproducts == ho.mvproducts
     match_eigs(P.eigenvalues, Po.eigenvalues, 1e-7)
+
+
+# ---------------------------------------- BASELINE configs against the oracle at the sizes SURVEY 8(d) asks for
+def test_full_size_cfg2_solve_matches_oracle():
+    """BASELINE cfg 2 at FULL size (n = 1e6, 16 nnz/row, nev 20, maxdim 40, :LM, tol 1e-6), the matrix and start vector
+    of bench.py: the complete solve against the oracle from the same v1 - `mvproducts` within one restart
+    (maxdim - mindim = 20), eigenvalues <= 10 tol |lambda|, ||A Q - Q R|| <= n tol with an independent mat-vec."""
+    import bench
+
+    n = bench.N_PER_GPU
+    indptr, indices, data = bench.make_shard(n, 0, n)
+    v1 = bench.make_v1(n, 0, n)
+    A = sp.csr_matrix((data, indices, indptr), shape=(n, n))
+    P, hist = b2a.partialschur(A, nev=bench.NEV, mindim=bench.MINDIM, maxdim=bench.MAXDIM, which=bench.WHICH,
+                               tol=bench.TOL, v1=v1)
+    Po, ho = oracle.partialschur(A, v1=v1, nev=bench.NEV, mindim=bench.MINDIM, maxdim=bench.MAXDIM, which=bench.WHICH,
+                                 tol=bench.TOL)
+    assert hist.converged and ho.converged and hist.nconverged == ho.nconverged
+    assert abs(hist.mvproducts - ho.mvproducts) <= bench.MAXDIM - bench.MINDIM, (hist.mvproducts, ho.mvproducts)
+    match_eigs(P.eigenvalues, Po.eigenvalues, 10 * bench.TOL)
+    Q = P.Q
+    assert np.linalg.norm(A @ Q - Q @ P.R) < n * bench.TOL
+    assert np.linalg.norm(Q.T @ Q - np.eye(Q.shape[1])) < 1000 * EPS
+    P.workspace.close()
+
+
+def test_cfg3_stencil_64_cubed_scale_matches_oracle():
+    """cfg 3 at the 64^3 scale SURVEY 8(d) asks for (7-point stencil, nev 10, maxdim 20, :SR, tol 1e-6; the oracle
+    needs ~330 restarts / ~1850 mat-vecs and ~25 s here).  Anisotropic 64 x 62 x 60 grid: simple eigenvalues, so the
+    restart path is comparable (see test_stencil_smallest_real_matches_oracle for why the isotropic one is not)."""
+    nx, ny, nz = 64, 62, 60
+    w = (1.0, 1.37, 1.83)
+    A = stencil3d(nx, ny, nz, *w)
+    lam = [wi * (2 - 2 * np.cos(np.arange(1, n + 1) * np.pi / (n + 1))) for wi, n in zip(w, (nx, ny, nz))]
+    exact = np.sort((lam[0][:, None, None] + lam[1][None, :, None] + lam[2][None, None, :]).ravel())
+    v1 = np.random.default_rng(45).random(A.shape[0])
+    P, hist = b2a.partialschur(A, nev=10, which="SR", tol=1e-6, v1=v1, restarts=1000)
+    Po, ho = oracle.partialschur(A, v1=v1, nev=10, which="SR", tol=1e-6, restarts=1000)
+    assert hist.converged and ho.converged and hist.nconverged == ho.nconverged == 10
+    # hundreds of restarts: rounding differences shift single locking events by a restart or two
+    assert abs(hist.mvproducts - ho.mvproducts) <= 0.1 * ho.mvproducts, (hist.mvproducts, ho.mvproducts)
+    assert np.allclose(np.sort(P.eigenvalues.real), exact[:10], atol=1e-5)
+    match_eigs(P.eigenvalues, Po.eigenvalues, 1e-5)
+    assert np.linalg.norm(A @ P.Q - P.Q @ P.R) < A.shape[0] * 1e-6
+    P.workspace.close()
+
+
+def test_cfg3_laplacian_128_cubed_capped_restarts_properties():
+    """cfg 3 at 128^3 (n = 2.1e6; does not converge within a bounded test - SURVEY 8(d) says so for 512^3): with the
+    restart budget capped, what IS returned must satisfy the reference's own invariants - locked Schur vectors
+    orthonormal, ||A Q - Q R|| <= n tol, every Ritz value inside the spectrum of the symmetric operator."""
+    N = 128
+    A = laplacian3d(N)
+    v1 = np.random.default_rng(46).random(N ** 3)
+    P, hist = b2a.partialschur(A, nev=10, which="SR", tol=1e-6, v1=v1, restarts=40)
+    assert hist.restarts == 40 or hist.converged
+    assert hist.mvproducts >= 10 + 40 * 5  # every restart expands by at least maxdim - k >= 5 steps... a real run
+    lam_min = 3 * (2 - 2 * np.cos(np.pi / (N + 1)))
+    lam_max = 3 * (2 - 2 * np.cos(N * np.pi / (N + 1)))
+    if hist.nconverged:
+        Q = P.Q
+        assert np.linalg.norm(Q.T @ Q - np.eye(Q.shape[1])) < 1000 * EPS
+        assert np.linalg.norm(A @ Q - Q @ P.R) < A.shape[0] * 1e-6
+        assert np.all(P.eigenvalues.real >= lam_min - 1e-6) and np.all(P.eigenvalues.real <= lam_max + 1e-6)
+    # the retained Krylov basis (columns 1 .. k+1, k >= mindim = 10) stays orthonormal over all the restarts
+    V = P.workspace.get_cols(1, 11)
+    assert np.abs(V.T @ V - np.eye(11)).max() < 1e-12
+    P.workspace.close()
