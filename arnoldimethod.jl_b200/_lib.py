@@ -16,9 +16,10 @@ F64, C64 = 0, 1
 WHICH = {"LM": 0, "LR": 1, "SR": 2, "LI": 3, "SI": 4}
 INIT_NONE, INIT_RAND, INIT_KEEP = 0, 1, 2
 KERNEL_KINDS = ("spmv", "cgs_dots", "cgs_update", "cgs_finish", "rotate", "fill", "cgs_sweep", "xchg")
-OK, ERR_ARGUMENT, ERR_DIMENSION, ERR_CUDA, ERR_NCCL, ERR_OOM, ERR_QR, ERR_INTERNAL, ERR_CALLBACK = (
-    0, -1, -2, -3, -4, -5, -6, -7, -8,
+OK, ERR_ARGUMENT, ERR_DIMENSION, ERR_CUDA, ERR_NCCL, ERR_OOM, ERR_QR, ERR_INTERNAL, ERR_CALLBACK, ERR_SOLVE = (
+    0, -1, -2, -3, -4, -5, -6, -7, -8, -9,
 )
+SOLVE_CG = 0
 
 
 class Stats(C.Structure):
@@ -83,6 +84,8 @@ SIGNATURES = {
     "b2a_csr_create_device": (_i, [_vp, _i, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _pvp]),
     "b2a_csc_create": (_i, [_vp, _i, _i64, _i64, _vp, _vp, _vp, _i, _i, _i, _pvp]),
     "b2a_op_from_callback": (_i, [_vp, _i, _i64, _i64, MATVEC_FN, _vp, _pvp]),
+    "b2a_op_shift_invert": (_i, [_vp, _vp, _d, _d, _i, _d, _i, _pvp]),
+    "b2a_op_solve_stats": (_i, [_vp, _pi64, _pi64, _pd]),
     "b2a_op_destroy": (_i, [_vp]),
     "b2a_op_bytes": (_i, [_vp, _pd]),
     "b2a_ws_create": (_i, [_vp, _i, _i64, _i64, _i64, _i, _pvp]),

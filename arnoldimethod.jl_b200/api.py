@@ -245,6 +245,25 @@ class Operator:
 
         return cls.from_callback(ctx, dt, n, n, cb)
 
+    @classmethod
+    def shift_invert(cls, A, sigma=0.0, rtol=1e-13, maxit=10000):
+        """The linear map ``x -> (A - sigma I) \\ x`` on the device (docs/src/index.md:234-262 builds it from a
+        factorisation and LinearMaps.jl): Jacobi-preconditioned CG on the CSR mat-vec of ``A``, for a Hermitian positive
+        definite ``A - sigma I``.  ``partialschur(op, which="LM")`` then finds the eigenvalues of ``A`` nearest
+        ``sigma`` as ``sigma + 1 / theta``.  ``A`` (an ``Operator``) must stay alive."""
+        sigma = complex(sigma)
+        h = C.c_void_p()
+        L.check(L.lib().b2a_op_shift_invert(A.ctx._h, A._h, sigma.real, sigma.imag, L.SOLVE_CG, float(rtol), int(maxit),
+                                            C.byref(h)))
+        return cls(A.ctx, h, A.dtype, A.n_local, A.n_global, A.row_offset, keep=(A,))
+
+    @property
+    def solve_stats(self):
+        """(solves, inner iterations, worst relative residual) of a shift-and-invert operator."""
+        a, b, w = C.c_int64(), C.c_int64(), C.c_double()
+        L.check(L.lib().b2a_op_solve_stats(self._h, C.byref(a), C.byref(b), C.byref(w)))
+        return a.value, b.value, w.value
+
     @property
     def bytes_per_matvec(self):
         v = C.c_double()

@@ -49,7 +49,8 @@ def needs_build():
 def build(force=False, verbose=False, ptxas_info=False):
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, *SOURCES, "-o", LIB]
+    tmp = LIB + ".building"  # build beside, then rename: a snapshot of the tree never sees a half-written library
+    cmd = [_nvcc(), *NVCC_FLAGS, *SOURCES, "-o", tmp]
     if ptxas_info:
         cmd[1:1] = ["-Xptxas", "-v"]
     if verbose:
@@ -57,7 +58,10 @@ def build(force=False, verbose=False, ptxas_info=False):
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed building libb200arnoldi.so")
+    os.replace(tmp, LIB)
     if verbose or ptxas_info:
         sys.stderr.write(res.stdout + res.stderr)
     return LIB

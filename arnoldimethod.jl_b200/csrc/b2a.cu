@@ -36,6 +36,7 @@
 #include "kernels_cgs_sweep.cuh"
 #include "kernels_rotate.cuh"
 #include "kernels_rotate_mma.cuh"
+#include "kernels_solve.cuh"
 #include "kernels_spmv.cuh"
 #include "kernels_spmv_tma.cuh"
 #include "peer_comm.cuh"
@@ -243,7 +244,7 @@ static void prof_collect(b2a_ctx *c, const int *info, int info_base, int info_co
   c->prof_pending.clear();
 }
 
-enum OpKind { OP_CSR = 0, OP_CSC_SCATTER = 1, OP_CALLBACK = 2 };
+enum OpKind { OP_CSR = 0, OP_CSC_SCATTER = 1, OP_CALLBACK = 2, OP_SHIFT_INVERT = 3 };
 
 struct b2a_op {
   b2a_ctx *ctx = nullptr;
@@ -270,6 +271,16 @@ struct b2a_op {
   int64_t owner_W = 0;  // rows per rank of the uniform partition the blocks were cut for
   b2a_matvec_fn fn = nullptr;
   void *user = nullptr;
+  // shift-and-invert (kernels_solve.cuh): inner operator, shift, work vectors d | r | z | p | q (n_local each)
+  b2a_op *inner = nullptr;
+  double sigma_re = 0.0, sigma_im = 0.0, solve_rtol = 1e-13;
+  int solve_maxit = 10000;
+  void *solve_work = nullptr;
+  b2a::CgState *cg = nullptr;
+  double2 *cg_partials = nullptr;
+  b2a::CgState *cg_host = nullptr;  // pinned read-back of the solver state
+  int64_t solves = 0, solve_iters = 0;
+  double solve_worst = 0.0;
 };
 
 struct b2a_ws {
@@ -845,8 +856,8 @@ template <class DT, int LPR>
 static cudaError_t launch_spmv_owner_fused_e(b2a_op *A, const DT *x_own, const DT *x_buf, DT *y, const int *poison,
                                              cudaStream_t st, const XWait &xw) {
   // entries per lane of one (row, owner block) segment
+  // (E = 4 with U = 4 rows per lane group measured slower than one launch per block at N = 2: register pressure)
   const double per_lane = (double)A->nnz / std::max<double>(1.0, (double)A->n_local * A->nblocks) / LPR;
-  if (per_lane >= 3.0) return launch_spmv_owner_fused_inst<DT, LPR, 4>(A, x_own, x_buf, y, poison, st, xw);
   if (per_lane >= 1.5) return launch_spmv_owner_fused_inst<DT, LPR, 2>(A, x_own, x_buf, y, poison, st, xw);
   return launch_spmv_owner_fused_inst<DT, LPR, 1>(A, x_own, x_buf, y, poison, st, xw);
 }
@@ -990,6 +1001,82 @@ template <class DT> static int enqueue_xchg(b2a_ws *ws, const DT *xl, unsigned l
   return B2A_OK;
 }
 
+// plain CSR mat-vec on raw device vectors (inner operator of a shift-and-invert map; single GPU)
+template <class DT> static int spmv_plain(b2a_ctx *ctx, b2a_op *A, const DT *x, DT *y, const int *poison) {
+  XWait xw;
+  cudaError_t le = cudaSuccess;
+  switch (A->lpr) {
+    case 1: {
+      if (A->nblocks > 1) {
+        le = launch_spmv_blocked<DT, 2>(A, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches);
+        break;
+      }
+      const int64_t grid = std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, cdiv(A->n_local, 256)));
+      b2a::spmv_csr_scalar_kernel<DT, false><<<(unsigned)grid, 256, 0, ctx->stream>>>(
+          A->n_local, A->d_ptr, A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x, y, poison, xw, 0);
+      break;
+    }
+    case 2: le = launch_spmv_vec<DT, 2>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
+    case 4: le = launch_spmv_vec<DT, 4>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
+    case 8: le = launch_spmv_vec<DT, 8>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
+    case 16: le = launch_spmv_vec<DT, 16>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
+    default: le = launch_spmv_vec<DT, 32>(A, x, y, poison, ctx->stream, ctx->num_sms, xw); break;
+  }
+  ctx->launches++;
+  CUDA_TRY(le);
+  CUDA_TRY(cudaGetLastError());
+  return B2A_OK;
+}
+
+// y = (A - sigma I)^{-1} b by Jacobi-preconditioned CG (kernels_solve.cuh).  Iterations are enqueued in chunks; the
+// device raises `done` itself, the host looks once per chunk.
+template <class DT> static int enqueue_shift_invert(b2a_ws *ws, b2a_op *S, const DT *b, DT *y) {
+  b2a_ctx *ctx = ws->ctx;
+  b2a_op *A = S->inner;
+  const int64_t n = S->n_local;
+  const int *poison = &ws->state->poison;
+  DT *d = reinterpret_cast<DT *>(S->solve_work);
+  DT *r = d + n, *z = r + n, *p = z + n, *q = p + n;
+  const DT sigma = b2a::make_scalar<DT>(S->sigma_re, S->sigma_im);
+  const int has_sigma = (S->sigma_re != 0.0 || S->sigma_im != 0.0) ? 1 : 0;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 4, cdiv(n, b2a::kSolveThreads)));
+  prof_begin(ctx, B2A_K_SPMV, 0.0);
+  b2a::cg_init_kernel<DT><<<grid, b2a::kSolveThreads, 0, ctx->stream>>>(n, b, d, y, r, z, p, S->cg_partials, S->cg,
+                                                                        S->solve_rtol * S->solve_rtol, poison);
+  ctx->launches++;
+  CUDA_TRY(cudaGetLastError());
+  int it = 0;
+  bool finished = false;
+  while (!finished) {
+    const int chunk = std::min(32, S->solve_maxit - it);
+    for (int c = 0; c < chunk; ++c) {
+      B2A_TRY(spmv_plain<DT>(ctx, A, p, q, poison));
+      b2a::cg_pq_kernel<DT><<<grid, b2a::kSolveThreads, 0, ctx->stream>>>(n, p, q, sigma, has_sigma, S->cg_partials,
+                                                                          S->cg, poison);
+      b2a::cg_update_kernel<DT><<<grid, b2a::kSolveThreads, 0, ctx->stream>>>(n, p, q, d, y, r, z, S->cg_partials,
+                                                                              S->cg, poison);
+      b2a::cg_p_kernel<DT><<<grid, b2a::kSolveThreads, 0, ctx->stream>>>(n, z, p, S->cg, poison);
+      ctx->launches += 3;
+    }
+    it += chunk;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(S->cg_host, S->cg, sizeof(b2a::CgState), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    finished = S->cg_host->done != 0 || it >= S->solve_maxit;
+  }
+  prof_end(ctx);
+  const b2a::CgState &st = *S->cg_host;
+  S->solves += 1;
+  S->solve_iters += st.iters;
+  const double rel = st.bb > 0.0 ? std::sqrt(st.rr / st.bb) : 0.0;
+  S->solve_worst = std::max(S->solve_worst, rel);
+  if (st.done == 2) return fail(B2A_ERR_SOLVE, "shift-and-invert: conjugate gradients broke down (p' (A - sigma I) p == 0; is the shifted operator definite?)");
+  if (st.done == 0)
+    return fail(B2A_ERR_SOLVE, "shift-and-invert: inner solve did not converge in " + std::to_string(S->solve_maxit) +
+                                   " iterations (relative residual " + std::to_string(rel) + ")");
+  return B2A_OK;
+}
+
 // y = A x for the local rows; x_local / y are workspace columns.
 template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, int jdst0) {
   b2a_ctx *ctx = ws->ctx;
@@ -1001,6 +1088,7 @@ template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, 
     if (rc != 0) return fail(B2A_ERR_CALLBACK, "matvec callback returned " + std::to_string(rc));
     return B2A_OK;
   }
+  if (A->kind == OP_SHIFT_INVERT) return enqueue_shift_invert<DT>(ws, A, xl, y);
   const DT *x = xl;
   XWait xw;
   bool owner_passes = false;
@@ -1414,7 +1502,7 @@ static double cgs_pass_bytes(const b2a_ws *ws, int j) {
 static double scal_bytes(const b2a_ws *ws) { return 2.0 * (double)ws->n_local * (double)ws->esz; }
 
 static double op_bytes(const b2a_op *A) {
-  if (A->kind == OP_CALLBACK) return 0.0;
+  if (A->kind == OP_CALLBACK || A->kind == OP_SHIFT_INVERT) return 0.0;
   const double s = (double)dtype_size(A->dtype);
   const double nptr = (A->kind == OP_CSC_SCATTER ? A->n_global : A->n_local) + 1.0;
   return (double)A->nnz * (s + 4.0) + 8.0 * nptr + 2.0 * (double)A->n_local * s;
@@ -1910,6 +1998,13 @@ int b2a_op_destroy(b2a_op *op) {
     cudaSetDevice(op->ctx->device);
     dev_free(op->ctx, op->d_tile_row);
   }
+  if (op->kind == OP_SHIFT_INVERT) {
+    cudaSetDevice(op->ctx->device);
+    dev_free(op->ctx, op->solve_work);
+    dev_free(op->ctx, op->cg);
+    dev_free(op->ctx, op->cg_partials);
+    if (op->cg_host) cudaFreeHost(op->cg_host);
+  }
   delete op;
   return B2A_OK;
 }
@@ -2040,7 +2135,13 @@ static int validate_structure(b2a_ctx *ctx, const int64_t *d_ptr, int64_t n_ptr,
 static int build_owner_blocks(b2a_ctx *ctx, b2a_op *op) {
   const int P = ctx->world;
   if (P < 2 || P > b2a::kMaxOwnerBlocks || op->n_local <= 0 || op->nnz <= 0) return B2A_OK;
-  if (getenv("B2A_OWNER_BLOCKS") && getenv("B2A_OWNER_BLOCKS")[0] == '0') return B2A_OK;
+  // Measured on 2 x B200 (bench.py, profiles/r2_bench_n2_variants.txt): with ONE remote slice the 8 MB transfer takes
+  // 23 us and a single pass that waits for it (105 us) beats two passes (114 us: every pass re-reads the row
+  // pointers, read-modify-writes y and pays its own ramp-up) and the all-blocks-in-one-launch kernel.  Owner blocks
+  // are cut from three ranks on, where the exchange is long enough to be worth hiding.  B2A_OWNER_BLOCKS=0/1 forces.
+  bool want = P >= 3;
+  if (const char *e = getenv("B2A_OWNER_BLOCKS")) want = e[0] != '0';
+  if (!want) return B2A_OK;
   const int64_t W = cdiv(op->n_global, P);
   if (op->row_offset != (int64_t)ctx->rank * W) return B2A_OK;
   if (op->n_local != std::min<int64_t>(W, op->n_global - op->row_offset)) return B2A_OK;
@@ -2323,6 +2424,71 @@ int b2a_op_from_callback(b2a_ctx *ctx, int dtype, int64_t n_rows_local, int64_t 
   op->user = user;
   op->owns = false;
   *out = op;
+  return B2A_OK;
+}
+
+int b2a_op_shift_invert(b2a_ctx *ctx, b2a_op *A, double sigma_re, double sigma_im, int method, double rtol, int maxit,
+                        b2a_op **out) {
+  if (!ctx || !A || !out) return fail(B2A_ERR_ARGUMENT, "NULL argument");
+  ARG_CHECK(A->ctx == ctx, "operator belongs to a different context");
+  ARG_CHECK(method == B2A_SOLVE_CG, "unknown inner solver");
+  ARG_CHECK(ctx->world == 1 && A->kind == OP_CSR && !A->owner_blocks,
+            "shift-and-invert needs a single-GPU CSR operator (CSC inputs: upload with mode 0)");
+  ARG_CHECK(A->dtype == B2A_C64 || sigma_im == 0.0, "a complex shift needs a ComplexF64 operator");
+  // the diagonal scan of the preconditioner walks ONE row-pointer array
+  ARG_CHECK(A->nblocks == 1, "shift-and-invert: column-blocked operators are not supported (set B2A_SPMV_BLOCK_MB=0)");
+  CUDA_TRY(cudaSetDevice(ctx->device));
+  b2a_op *op = new b2a_op();
+  op->ctx = ctx;
+  op->dtype = A->dtype;
+  op->kind = OP_SHIFT_INVERT;
+  op->n_local = A->n_local;
+  op->n_global = A->n_global;
+  op->row_offset = A->row_offset;
+  op->owns = false;
+  op->inner = A;
+  op->sigma_re = sigma_re;
+  op->sigma_im = sigma_im;
+  op->solve_rtol = rtol > 0.0 ? rtol : 1e-13;
+  op->solve_maxit = maxit > 0 ? maxit : 10000;
+  const size_t es = dtype_size(A->dtype);
+  const int64_t n = std::max<int64_t>(A->n_local, 1);
+  const unsigned pgrid = (unsigned)ctx->num_sms * 4;
+  cudaError_t e = dev_alloc(ctx, &op->solve_work, (size_t)5 * n * es);
+  if (e == cudaSuccess) e = dev_alloc(ctx, reinterpret_cast<void **>(&op->cg), sizeof(b2a::CgState));
+  if (e == cudaSuccess) e = dev_alloc(ctx, reinterpret_cast<void **>(&op->cg_partials), sizeof(double2) * 2 * pgrid);
+  if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void **>(&op->cg_host), sizeof(b2a::CgState));
+  if (e == cudaSuccess) e = cudaMemsetAsync(op->cg, 0, sizeof(b2a::CgState), ctx->stream);
+  if (e == cudaSuccess) {
+    // Jacobi preconditioner of the shifted operator
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 8, cdiv(n, 256)));
+    if (A->dtype == B2A_F64)
+      b2a::shifted_diag_kernel<double><<<grid, 256, 0, ctx->stream>>>(A->n_local, A->d_ptr, A->d_idx,
+                                                                      reinterpret_cast<const double *>(A->d_vals),
+                                                                      A->row_offset, sigma_re,
+                                                                      reinterpret_cast<double *>(op->solve_work));
+    else
+      b2a::shifted_diag_kernel<cdouble><<<grid, 256, 0, ctx->stream>>>(A->n_local, A->d_ptr, A->d_idx,
+                                                                       reinterpret_cast<const cdouble *>(A->d_vals),
+                                                                       A->row_offset, make_double2(sigma_re, sigma_im),
+                                                                       reinterpret_cast<cdouble *>(op->solve_work));
+    ctx->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    b2a_op_destroy(op);
+    CUDA_TRY(e);
+  }
+  *out = op;
+  return B2A_OK;
+}
+
+int b2a_op_solve_stats(b2a_op *op, int64_t *solves, int64_t *iterations, double *worst_relres) {
+  if (!op || op->kind != OP_SHIFT_INVERT) return fail(B2A_ERR_ARGUMENT, "not a shift-and-invert operator");
+  if (solves) *solves = op->solves;
+  if (iterations) *iterations = op->solve_iters;
+  if (worst_relres) *worst_relres = op->solve_worst;
   return B2A_OK;
 }
 

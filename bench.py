@@ -389,6 +389,19 @@ def run_gpu(args):
     ws.close()
     op.close()
 
+    if os.environ.get("B2A_BENCH_QUICK") == "1":
+        # variant sweeps on multi-GPU leases (tools/gpu_r2_multi8.sh): device-timed arm only, one compact line
+        if rank == 0:
+            print(json.dumps({"quick": True, "n_gpus": world, "ms_per_step": ms_total / max(args.steps, 1),
+                              "value": value, "mvproducts": mv // max(args.steps, 1), "converged": converged,
+                              "hbm_frac_aggregate": round(hbm_gbs / (peak * world), 4),
+                              "kernels_us": {k: (v["launches"], v["avg_us"]) for k, v in kern.items()},
+                              "env": {k: v for k, v in os.environ.items() if k.startswith("B2A_")}}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
     # ---------------- e2e arm: host CSR in pinned memory -> upload -> solve -> download Q, R, eigenvalues
     def e2e_step():
         op2 = b2a.Operator.from_csr_arrays(ctx, indptr_p, indices_p, data_p, n_global, row_offset=off)

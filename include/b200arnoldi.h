@@ -47,7 +47,8 @@ enum b2a_status {
   B2A_ERR_OOM = -5,
   B2A_ERR_QR = -6, /* "QR algorithm did not converge" (src/schurfact.jl:406)           */
   B2A_ERR_INTERNAL = -7,
-  B2A_ERR_CALLBACK = -8 /* user mat-vec callback returned non-zero                      */
+  B2A_ERR_CALLBACK = -8, /* user mat-vec callback returned non-zero                     */
+  B2A_ERR_SOLVE = -9     /* inner solve of a shift-and-invert operator did not converge     */
 };
 
 enum b2a_dtype { B2A_F64 = 0, B2A_C64 = 1 };
@@ -138,6 +139,21 @@ int b2a_csc_create(b2a_ctx *ctx, int dtype, int64_t n_global, int64_t nnz, const
 typedef int (*b2a_matvec_fn)(void *user, const void *x_dev, void *y_dev, int64_t n_local, void *stream);
 int b2a_op_from_callback(b2a_ctx *ctx, int dtype, int64_t n_rows_local, int64_t n_global,
                          b2a_matvec_fn matvec, void *user, b2a_op **out);
+
+/* Shift-and-invert operator  y = (A - sigma I)^{-1} x  on the device.
+ * The reference leaves spectral transformations to the user: docs/src/index.md:234-262 ("Shift-and-invert with
+ * LinearMaps.jl") and bench/partial_schur.jl:11-35 wrap a factorisation in a linear map and hand that to
+ * partialschur with which = :LM; eigenvalues of A nearest sigma are then sigma + 1 / theta.  Here the map is an
+ * iterative solve built on the CSR mat-vec of `A` (single GPU, CSR operator; `A` must outlive the result):
+ *   method B2A_SOLVE_CG = Jacobi-preconditioned conjugate gradients, for A - sigma I Hermitian positive definite
+ *   (e.g. the smallest modes of a Laplacian-type operator).  Every mat-vec with the result runs the inner solve to
+ *   ||r|| <= rtol ||x|| (rtol <= 0: 1e-13) in at most maxit iterations (maxit <= 0: 10000); a solve that does not
+ *   get there makes the mat-vec - and the partialschur call around it - fail with B2A_ERR_SOLVE. */
+enum { B2A_SOLVE_CG = 0 };
+int b2a_op_shift_invert(b2a_ctx *ctx, b2a_op *A, double sigma_re, double sigma_im, int method, double rtol,
+                        int maxit, b2a_op **out);
+/* inner-solver statistics of a shift-and-invert operator since its creation */
+int b2a_op_solve_stats(b2a_op *op, int64_t *solves, int64_t *iterations, double *worst_relres);
 
 int b2a_op_destroy(b2a_op *op);
 /* algorithmic bytes one mat-vec moves (nnz*(s+4) + 8*(n+1) + 2*n*s) */

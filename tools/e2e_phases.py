@@ -54,7 +54,7 @@ def step(timers):
     ctx.synchronize(); t6 = time.perf_counter(); timers["free"] += t6 - t5
 
 
-for rep in range(4):
+for rep in range(3):
     timers = {k: 0.0 for k in PHASES}
     N = 5
     if world > 1:

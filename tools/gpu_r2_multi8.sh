@@ -1,13 +1,33 @@
 #!/bin/bash
-# round 2, 8-GPU call: parity at N = 8 (small + BASELINE size), bench at N = 4 / 8 (+ round-1 exchange at N = 8),
+# round 2, 8-GPU call: parity at N = 8 (small + BASELINE size), exchange variants at N = 4 / 8, full bench lines,
 # BASELINE cfg 5 at its true size (north star), e2e phases at N = 8
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
 nvidia-smi topo -m > gpurun_out/r2_topo.txt 2>&1
 timeout 240 $TR --nproc-per-node 8 --master-port 29701 tests/dist_gpu_check.py > gpurun_out/r2_dist_check_n8.log 2>&1
 grep -E "world=|OK" gpurun_out/r2_dist_check_n8.log | cut -c1-300
-timeout 400 $TR --nproc-per-node 8 --master-port 29702 tests/dist_gpu_check.py --big 1000000 > gpurun_out/r2_dist_big_n8.log 2>&1
-grep -E "^\{|OK" gpurun_out/r2_dist_big_n8.log | cut -c1-700
+timeout 300 $TR --nproc-per-node 8 --master-port 29702 tests/dist_gpu_check.py --big 1000000 --dump gpurun_out/r2_big_n8.npz > gpurun_out/r2_dist_big_n8.log 2>&1
+grep -E "^\{|DUMPED|Error|error" gpurun_out/r2_dist_big_n8.log | cut -c1-700
+: > gpurun_out/r2_variants_n48.txt
+port=29710
+for N in 8; do
+  for v in "B2A_OWNER_FUSED=1" "B2A_OWNER_FUSED=0" "B2A_OWNER_BLOCKS=0" "B2A_XCHG=0"; do
+    port=$((port+1))
+    env B2A_BENCH_QUICK=1 $v timeout 120 $TR --nproc-per-node $N --master-port $port bench.py --gpus $N --steps 6 --warmup 3 2>/dev/null | grep "^{" >> gpurun_out/r2_variants_n48.txt
+  done
+done
+BEST=$(python - <<'PY'
+import json,sys
+best=None
+for l in open('gpurun_out/r2_variants_n48.txt'):
+    d=json.loads(l); e={k:v for k,v in d['env'].items() if k!='B2A_BENCH_QUICK'}
+    print('N',d['n_gpus'],e,'ms/solve',round(d['ms_per_step'],2),'frac',d['hbm_frac_aggregate'],d['kernels_us'], file=sys.stderr)
+    if d.get('converged') and (best is None or d['ms_per_step']<best[0]): best=(d['ms_per_step'],e)
+print(' '.join(f'{k}={v}' for k,v in (best[1] if best else {}).items()))
+PY
+)
+echo "best variant at N=8: $BEST"
+export $BEST
 summ() {
 python - "$1" "$2" <<'PY'
 import json,sys
@@ -19,13 +39,11 @@ except Exception as e:
     print(sys.argv[1], 'FAILED', e)
 PY
 }
-timeout 200 $TR --nproc-per-node 8 --master-port 29703 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r2_bench_n8.json 2> gpurun_out/r2_bench_n8.err
+timeout 200 $TR --nproc-per-node 8 --master-port 29731 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r2_bench_n8.json 2> gpurun_out/r2_bench_n8.err
 summ "N=8 default" gpurun_out/r2_bench_n8.json
-CUDA_VISIBLE_DEVICES=0,1,2,3 timeout 200 $TR --nproc-per-node 4 --master-port 29704 bench.py --gpus 4 --steps 10 --warmup 3 > gpurun_out/r2_bench_n4.json 2> gpurun_out/r2_bench_n4.err
+CUDA_VISIBLE_DEVICES=0,1,2,3 timeout 200 $TR --nproc-per-node 4 --master-port 29732 bench.py --gpus 4 --steps 10 --warmup 3 > gpurun_out/r2_bench_n4.json 2> gpurun_out/r2_bench_n4.err
 summ "N=4 default" gpurun_out/r2_bench_n4.json
-B2A_XCHG=0 timeout 200 $TR --nproc-per-node 8 --master-port 29705 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r2_bench_n8_push.json 2> gpurun_out/r2_bench_n8_push.err
-summ "N=8 round-1 exchange" gpurun_out/r2_bench_n8_push.json
-timeout 500 $TR --nproc-per-node 8 --master-port 29706 tools/cfg_dist_bench.py cfg5 --residual --restarts 200 > gpurun_out/r2_cfg5_n8.json 2> gpurun_out/r2_cfg5_n8.err
+timeout 500 $TR --nproc-per-node 8 --master-port 29733 tools/cfg_dist_bench.py cfg5 --residual --restarts 200 > gpurun_out/r2_cfg5_n8.json 2> gpurun_out/r2_cfg5_n8.err
 grep "^{" gpurun_out/r2_cfg5_n8.json | cut -c1-1800; tail -3 gpurun_out/r2_cfg5_n8.err | cut -c1-300
-timeout 200 $TR --nproc-per-node 8 --master-port 29707 tools/e2e_phases.py > gpurun_out/r2_e2e_phases_n8.log 2>&1
+timeout 200 $TR --nproc-per-node 8 --master-port 29735 tools/e2e_phases.py > gpurun_out/r2_e2e_phases_n8.log 2>&1
 grep "^{" gpurun_out/r2_e2e_phases_n8.log
