@@ -114,6 +114,7 @@ SIGNATURES = {
     "b2a_host_restart": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i, _d, _i, _i, _pi, _pi, _pi, _vp, _vp]),
     "b2a_host_sortschur": (_i, [_i, _vp, _i, _vp, _i, _i, _i, _i]),
     "b2a_host_col_block_plan": (_i, [_i, _i64, _d, _d, _pi]),
+    "b2a_host_owner_group_plan": (_i, [_i, _i64, _i, _i, _pi, _pi, _pi]),
     "b2a_host_givens": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
 }
 

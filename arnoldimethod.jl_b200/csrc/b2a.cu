@@ -265,10 +265,12 @@ struct b2a_op {
   // column blocking (x larger than L2 and scattered columns): block-major CSR, d_ptr holds nblocks row-pointer
   // arrays of n_local+1 entries each (absolute positions in d_idx / d_vals)
   int nblocks = 1;
-  // row-sharded operators: the column blocks are the OWNER blocks of x (block b = columns of rank b), so that one
-  // launch per owner can start as soon as that rank's slice has arrived (staged exchange)
+  // row-sharded operators: the column blocks are OWNER GROUPS of x (block b = columns of the ranks rank + b G ..
+  // rank + b G + G - 1, in the order the staged exchange delivers their slices), about 32 MB of x each, so that one
+  // launch per group starts as soon as its slices have arrived and gathers from an L2-resident part of x
   bool owner_blocks = false;
   int64_t owner_W = 0;  // rows per rank of the uniform partition the blocks were cut for
+  int owner_G = 1;      // ranks per block
   b2a_matvec_fn fn = nullptr;
   void *user = nullptr;
   // shift-and-invert (kernels_solve.cuh): inner operator, shift, work vectors d | r | z | p | q (n_local each)
@@ -812,65 +814,24 @@ static cudaError_t launch_spmv_blocked(b2a_op *A, const DT *x, DT *y, const int 
   }
   return cudaSuccess;
 }
-// operator stored by OWNER block (row-sharded, staged exchange): pass 0 = this rank's own columns, gathered
-// straight from the workspace column (no wait, no copy); pass k = the columns of rank (rank + k) % P, gathered from
-// the exchange buffer once that rank's slice has arrived - the order in which the staged exchange delivers them
+// operator stored by OWNER GROUP (row-sharded, staged exchange): block b holds the columns of the ranks
+// rank + b G .. rank + b G + G - 1 (mod P), i.e. the slices in their order of arrival; one L2-hinted pass per block, each
+// waiting only for the slices of its own group, the first writing y and the others accumulating.
 template <class DT, int LPR>
-static cudaError_t launch_spmv_owner(b2a_op *A, const DT *x_local_shifted, const DT *x_buf, DT *y, const int *poison,
-                                     cudaStream_t st, int sms, const XWait &xw, int64_t *launches) {
-  const int P = xw.pv.P, me = xw.pv.rank;
-  for (int k = 0; k < P; ++k) {
-    const int owner = (me + k) % P;
-    const int64_t *rp = A->d_ptr + (size_t)owner * (A->n_local + 1);
-    cudaError_t e;
-    if (k == 0) {
-      XWait w;
-      e = launch_spmv_vec_one<DT, LPR, 2, false, false>(A, rp, x_local_shifted, y, poison, st, sms, w, 0);
-    } else {
-      XWait w = xw;
-      w.mode = 2;
-      w.owner = owner;
-      e = launch_spmv_vec_one<DT, LPR, 2, false, true>(A, rp, x_buf, y, poison, st, sms, w, 1);
-      ++*launches;
-    }
+static cudaError_t launch_spmv_groups(b2a_op *A, const DT *x_buf, DT *y, const int *poison, cudaStream_t st, int sms,
+                                      const XWait &xw, int64_t *launches) {
+  const int P = xw.pv.P, G = A->owner_G;
+  for (int b = 0; b < A->nblocks; ++b) {
+    const int64_t *rp = A->d_ptr + (size_t)b * (A->n_local + 1);
+    XWait w = xw;
+    w.mode = 4;
+    w.owner = b * G;
+    w.count = std::min(G, P - b * G);
+    const cudaError_t e = launch_spmv_vec_one<DT, LPR, 2, true, true>(A, rp, x_buf, y, poison, st, sms, w, b > 0 ? 1 : 0);
     if (e != cudaSuccess) return e;
+    if (b > 0) ++*launches;
   }
   return cudaSuccess;
-}
-// ... or all owner blocks in ONE launch (kernels_spmv.cuh spmv_owner_fused_kernel): row sums stay in registers across
-// the blocks.  Default; B2A_OWNER_FUSED=0 selects one launch per block.  Returns cudaErrorNotSupported when the lane
-// configuration has no instantiation (very dense rows) - the caller then takes the per-block launches.
-static bool g_owner_fused = !(getenv("B2A_OWNER_FUSED") && getenv("B2A_OWNER_FUSED")[0] == '0');
-template <class DT, int LPR, int E>
-static cudaError_t launch_spmv_owner_fused_inst(b2a_op *A, const DT *x_own, const DT *x_buf, DT *y, const int *poison,
-                                                cudaStream_t st, const XWait &xw) {
-  constexpr int U = 4;
-  const int64_t threads = cdiv(A->n_local, U) * LPR;
-  const int64_t grid = std::max<int64_t>(1, cdiv(threads, 256));  // every lane group owns <= U rows: no grid stride
-  if (grid > 2147483647LL) return cudaErrorNotSupported;
-  return launch_pdl(b2a::spmv_owner_fused_kernel<DT, LPR, U, E>, (unsigned)grid, 256u, 0, st, A->n_local,
-                    (const int64_t *)A->d_ptr, (const int32_t *)A->d_idx, reinterpret_cast<const DT *>(A->d_vals), x_own,
-                    x_buf, y, poison, xw);
-}
-template <class DT, int LPR>
-static cudaError_t launch_spmv_owner_fused_e(b2a_op *A, const DT *x_own, const DT *x_buf, DT *y, const int *poison,
-                                             cudaStream_t st, const XWait &xw) {
-  // entries per lane of one (row, owner block) segment
-  // (E = 4 with U = 4 rows per lane group measured slower than one launch per block at N = 2: register pressure)
-  const double per_lane = (double)A->nnz / std::max<double>(1.0, (double)A->n_local * A->nblocks) / LPR;
-  if (per_lane >= 1.5) return launch_spmv_owner_fused_inst<DT, LPR, 2>(A, x_own, x_buf, y, poison, st, xw);
-  return launch_spmv_owner_fused_inst<DT, LPR, 1>(A, x_own, x_buf, y, poison, st, xw);
-}
-template <class DT>
-static cudaError_t launch_spmv_owner_fused(b2a_op *A, const DT *x_own, const DT *x_buf, DT *y, const int *poison,
-                                           cudaStream_t st, const XWait &xw) {
-  switch (A->lpr) {
-    case 1:
-    case 2: return launch_spmv_owner_fused_e<DT, 2>(A, x_own, x_buf, y, poison, st, xw);
-    case 4: return launch_spmv_owner_fused_e<DT, 4>(A, x_own, x_buf, y, poison, st, xw);
-    case 8: return launch_spmv_owner_fused_e<DT, 8>(A, x_own, x_buf, y, poison, st, xw);
-    default: return cudaErrorNotSupported;
-  }
 }
 
 template <class DT, int LPR>
@@ -1101,14 +1062,13 @@ template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, 
     xw.pv = ws->peer;
     xw.want = seq;
     x = xbuf;
-    if (A->owner_blocks && A->kind == OP_CSR && ws->uniform_partition && ws->all_counts[0] == A->owner_W) {
-      owner_passes = true;
-    } else {
-      // operator not stored by owner block: own slice into the buffer (stream-ordered), then wait for all the others
-      CUDA_TRY(cudaMemcpyAsync(const_cast<DT *>(xbuf) + ws->row_offset, xl, (size_t)ws->n_local * sizeof(DT),
-                               cudaMemcpyDeviceToDevice, ctx->stream));
-      xw.mode = 3;
-    }
+    // own slice into the buffer (stream-ordered copy-engine transfer): every pass gathers from the one buffer
+    CUDA_TRY(cudaMemcpyAsync(const_cast<DT *>(xbuf) + ws->row_offset, xl, (size_t)ws->n_local * sizeof(DT),
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+    if (A->owner_blocks && A->kind == OP_CSR && ws->uniform_partition && ws->all_counts[0] == A->owner_W)
+      owner_passes = true;  // one pass per owner group, each waiting for its own slices
+    else
+      xw.mode = 3;  // single pass (or generic column blocks): wait for all the others first
   } else if (ctx->world > 1 && ws->peer.P > 1 && ws->peer_x) {
     // push model over NVLink peer memory: normally the normalising cgs_finish kernel of the previous step
     // has already pushed this column into every rank's x buffer; otherwise push it explicitly
@@ -1155,20 +1115,13 @@ template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, 
       default: launch_spmv_csc<DT, 32>(A, x, y, poison, ctx->stream, ctx->num_sms); break;
     }
   } else if (owner_passes) {
-    const DT *xls = xl - ws->row_offset;  // global column c of the own block -> workspace row c - row_offset
-    le = cudaErrorNotSupported;
-    if (g_owner_fused) {
-      XWait w = xw;
-      w.mode = 2;
-      le = launch_spmv_owner_fused<DT>(A, xls, x, y, poison, ctx->stream, w);
-    }
-    if (le == cudaErrorNotSupported) switch (A->lpr) {
+    switch (A->lpr) {
       case 1:
-      case 2: le = launch_spmv_owner<DT, 2>(A, xls, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches); break;
-      case 4: le = launch_spmv_owner<DT, 4>(A, xls, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches); break;
-      case 8: le = launch_spmv_owner<DT, 8>(A, xls, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches); break;
-      case 16: le = launch_spmv_owner<DT, 16>(A, xls, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches); break;
-      default: le = launch_spmv_owner<DT, 32>(A, xls, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches); break;
+      case 2: le = launch_spmv_groups<DT, 2>(A, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches); break;
+      case 4: le = launch_spmv_groups<DT, 4>(A, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches); break;
+      case 8: le = launch_spmv_groups<DT, 8>(A, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches); break;
+      case 16: le = launch_spmv_groups<DT, 16>(A, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches); break;
+      default: le = launch_spmv_groups<DT, 32>(A, x, y, poison, ctx->stream, ctx->num_sms, xw, &ctx->launches); break;
     }
   } else if (A->use_tma && ctx->world == 1 && A->nblocks == 1) {
     B2A_TRY(launch_spmv_tma<DT>(A, x, y, poison, ctx));
@@ -2128,24 +2081,42 @@ static int validate_structure(b2a_ctx *ctx, const int64_t *d_ptr, int64_t n_ptr,
   return B2A_OK;
 }
 
-// ---- owner blocks (row-sharded operators) --------------------------------------------------------------------
-// Reorder the uploaded shard block-major by owner rank of the column, on the device (kernels_blocks.cuh).  W = rows
-// per rank of the uniform partition, deduced from this rank's own block; if the block does not look like a uniform
-// partition the operator stays as it is (the mat-vec then waits for the whole exchange before its single pass).
+// ---- owner groups (row-sharded operators) --------------------------------------------------------------------
+// Reorder the uploaded shard block-major by the GROUP of ranks that owns the column, on the device
+// (kernels_blocks.cuh).  W = rows per rank of the uniform partition, deduced from this rank's own block; if the block
+// does not look like a uniform partition the operator stays as it is (the mat-vec then waits for the whole exchange
+// before its single pass).
+// ranks per owner group: as many slices of W rows as fit 32 MB of x, at least one, at most all
+static int owner_group_size(int64_t W, size_t es, int P) {
+  const int64_t slice = std::max<int64_t>(1, W * (int64_t)es);
+  return (int)std::min<int64_t>(P, std::max<int64_t>(1, (int64_t)(32.0 * 1048576.0) / slice));
+}
+
 static int build_owner_blocks(b2a_ctx *ctx, b2a_op *op) {
   const int P = ctx->world;
   if (P < 2 || P > b2a::kMaxOwnerBlocks || op->n_local <= 0 || op->nnz <= 0) return B2A_OK;
   // Measured on 2 x B200 (bench.py, profiles/r2_bench_n2_variants.txt): with ONE remote slice the 8 MB transfer takes
   // 23 us and a single pass that waits for it (105 us) beats two passes (114 us: every pass re-reads the row
-  // pointers, read-modify-writes y and pays its own ramp-up) and the all-blocks-in-one-launch kernel.  Owner blocks
-  // are cut from three ranks on, where the exchange is long enough to be worth hiding.  B2A_OWNER_BLOCKS=0/1 forces.
-  bool want = P >= 3;
+  // pointers, read-modify-writes y and pays its own ramp-up) and an all-blocks-in-one-launch kernel (147 us).
+  // B2A_OWNER_BLOCKS=0 switches the reordering off, B2A_OWNER_GROUP=<ranks per block> overrides the size rule below.
+  bool want = true;
   if (const char *e = getenv("B2A_OWNER_BLOCKS")) want = e[0] != '0';
   if (!want) return B2A_OK;
   const int64_t W = cdiv(op->n_global, P);
+  // ranks per block: as many as fit ~32 MB of x (the block size that measured best for the L2-blocked mat-vec,
+  // DESIGN 5); one block = no reordering (the mat-vec waits for the whole exchange, best up to 4 x 8 MB).
+  // Measured at N = 8 (profiles/r2_variants_n8.txt): blocks of ONE owner (8 MB, 8 passes or one fused launch)
+  // 316-319 us per mat-vec - every pass re-reads the row pointers and read-modify-writes y for 2 entries per row;
+  // no blocks 273 us, of which ~80 us wait for the exchange and ~190 us are gathers from a 64 MB x that no longer
+  // sits in L2 (89 us on one GPU with 8 MB).
+  int G = owner_group_size(W, dtype_size(op->dtype), P);
+  if (const char *e = getenv("B2A_OWNER_GROUP")) G = std::min(P, std::max(1, atoi(e)));
+  const int nb = (int)cdiv(P, G);
+  if (nb < 2) return B2A_OK;
   if (op->row_offset != (int64_t)ctx->rank * W) return B2A_OK;
   if (op->n_local != std::min<int64_t>(W, op->n_global - op->row_offset)) return B2A_OK;
-  const int64_t n = op->n_local, ld = n + 1, L = (int64_t)P * ld;
+  const int64_t n = op->n_local, ld = n + 1, L = (int64_t)nb * ld;
+  const b2a::OwnerGroups og{W, ctx->rank, P, G};
   const size_t es = dtype_size(op->dtype);
   int64_t *bptr = nullptr, *sums = nullptr;
   int32_t *bcol = nullptr;
@@ -2158,17 +2129,17 @@ static int build_owner_blocks(b2a_ctx *ctx, b2a_op *op) {
   if (e == cudaSuccess) e = cudaMemsetAsync(bptr, 0, (size_t)L * 8, ctx->stream);
   if (e == cudaSuccess) {
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 16, cdiv(n, 256)));
-    b2a::blk_count_kernel<<<grid, 256, 0, ctx->stream>>>(n, op->d_ptr, op->d_idx, W, bptr);
+    b2a::blk_count_kernel<<<grid, 256, 0, ctx->stream>>>(n, op->d_ptr, op->d_idx, og, bptr);
     b2a::scan_partial_kernel<<<(unsigned)nchunks, b2a::kScanThreads, 0, ctx->stream>>>(bptr, L, sums);
     b2a::scan_sums_kernel<<<1, b2a::kScanThreads, 0, ctx->stream>>>(sums, nchunks);
     b2a::scan_apply_kernel<<<(unsigned)nchunks, b2a::kScanThreads, 0, ctx->stream>>>(bptr, L, sums);
     if (op->dtype == B2A_F64)
       b2a::blk_scatter_kernel<double><<<grid, 256, 0, ctx->stream>>>(n, op->d_ptr, op->d_idx,
-                                                                     reinterpret_cast<const double *>(op->d_vals), W, P,
+                                                                     reinterpret_cast<const double *>(op->d_vals), og, nb,
                                                                      bptr, bcol, reinterpret_cast<double *>(bval));
     else
       b2a::blk_scatter_kernel<cdouble><<<grid, 256, 0, ctx->stream>>>(n, op->d_ptr, op->d_idx,
-                                                                      reinterpret_cast<const cdouble *>(op->d_vals), W, P,
+                                                                      reinterpret_cast<const cdouble *>(op->d_vals), og, nb,
                                                                       bptr, bcol, reinterpret_cast<cdouble *>(bval));
     ctx->launches += 5;
     e = cudaGetLastError();
@@ -2187,10 +2158,11 @@ static int build_owner_blocks(b2a_ctx *ctx, b2a_op *op) {
   op->d_ptr = bptr;
   op->d_idx = bcol;
   op->d_vals = bval;
-  op->nblocks = P;
+  op->nblocks = nb;
   op->owner_blocks = true;
   op->owner_W = W;
-  op->lpr = pick_lanes(op->nnz, n * P);
+  op->owner_G = G;
+  op->lpr = pick_lanes(op->nnz, n * nb);
   if (const char *env = getenv("B2A_SPMV_LPR")) op->lpr = atoi(env);
   op->use_tma = false;
   return B2A_OK;
@@ -3266,6 +3238,21 @@ int b2a_host_col_block_plan(int dtype, int64_t n_global, double nnz_per_row, dou
   if (!nblocks || n_global < 1) return fail(B2A_ERR_ARGUMENT, "bad argument");
   const size_t es = dtype_size(dtype);
   *nblocks = col_block_plan((double)n_global * (double)es, es, nnz_per_row, mean_col_distance * (double)es);
+  return B2A_OK;
+}
+
+int b2a_host_owner_group_plan(int dtype, int64_t n_global, int world, int rank, int *ranks_per_block, int *nblocks,
+                              int *block_of_owner) {
+  if (!ranks_per_block || !nblocks || n_global < 1 || world < 1 || rank < 0 || rank >= world)
+    return fail(B2A_ERR_ARGUMENT, "bad argument");
+  const int64_t W = cdiv(n_global, world);
+  const int G = owner_group_size(W, dtype_size(dtype), world);
+  *ranks_per_block = G;
+  *nblocks = (int)cdiv(world, G);
+  if (block_of_owner) {
+    const b2a::OwnerGroups og{W, rank, world, G};
+    for (int o = 0; o < world; ++o) block_of_owner[o] = ((o - og.me + og.P) % og.P) / og.G;
+  }
   return B2A_OK;
 }
 

@@ -2,9 +2,11 @@
 //   * validate_csr      index-range / monotonicity check of an uploaded CSR or CSC structure (the reference gets
 //                       this from the SparseMatrixCSC constructor; a malformed array must be an ArgumentError,
 //                       not an out-of-bounds gather)
-//   * owner-block build reorder the entries of a row shard BLOCK-MAJOR by the rank that owns the column
-//                       (block b = columns [b W, (b+1) W)), stable within a row, so that the row-sharded mat-vec
-//                       can run one pass per owner behind the staged x exchange (b2a.cu enqueue_matvec):
+//   * owner-group build reorder the entries of a row shard BLOCK-MAJOR by the GROUP of ranks that owns the column:
+//                       owner = col / W, block = ((owner - me) mod P) / G, i.e. block 0 = this rank's own columns
+//                       and those of the next G - 1 ranks in the order in which the staged exchange delivers their
+//                       slices, block 1 the next G ranks, ... - stable within a row - so that the row-sharded
+//                       mat-vec runs one L2-sized pass per group behind the arrivals (b2a.cu enqueue_matvec):
 //                       count -> flat inclusive scan -> scatter.  No library calls (no thrust / cub).
 #pragma once
 
@@ -32,17 +34,25 @@ __global__ void __launch_bounds__(256)
 }
 
 constexpr int kMaxOwnerBlocks = 16;
+struct OwnerGroups {
+  int64_t W;  // rows (= columns) per rank of the uniform partition
+  int me, P, G;
+};
+__device__ __forceinline__ int owner_block(const OwnerGroups &og, int32_t col) {
+  const int owner = (int)((int64_t)col / og.W);
+  return ((owner - og.me + og.P) % og.P) / og.G;
+}
 
 // bptr: nblocks x (n_rows + 1) int64, zero on entry; on exit bptr[b][r + 1] = entries of row r in block b
 __global__ void __launch_bounds__(256)
-    blk_count_kernel(int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind, int64_t W,
-                     int64_t *bptr) {
+    blk_count_kernel(int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                     OwnerGroups og, int64_t *bptr) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t ld = n_rows + 1;
   for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
     const int64_t s = rowptr[r], e = rowptr[r + 1];
     for (int64_t i = s; i < e; ++i) {
-      const int64_t b = (int64_t)colind[i] / W;
+      const int64_t b = owner_block(og, colind[i]);
       bptr[b * ld + r + 1] += 1;  // slot private to this thread
     }
   }
@@ -123,7 +133,7 @@ __global__ void __launch_bounds__(kScanThreads)
 template <class T>
 __global__ void __launch_bounds__(256)
     blk_scatter_kernel(int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
-                       const T *__restrict__ vals, int64_t W, int nblocks, const int64_t *__restrict__ bptr,
+                       const T *__restrict__ vals, OwnerGroups og, int nblocks, const int64_t *__restrict__ bptr,
                        int32_t *__restrict__ bcol, T *__restrict__ bval) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t ld = n_rows + 1;
@@ -133,7 +143,7 @@ __global__ void __launch_bounds__(256)
     const int64_t s = rowptr[r], e = rowptr[r + 1];
     for (int64_t i = s; i < e; ++i) {
       const int32_t c = colind[i];
-      const int b = (int)((int64_t)c / W);
+      const int b = owner_block(og, c);
       const int64_t dst = cur[b]++;
       bcol[dst] = c;
       bval[dst] = vals[i];

@@ -81,11 +81,14 @@ __device__ __forceinline__ cdouble ld_coh_hint(const cdouble *p, uint64_t pol) {
 //           kernel of the previous step stored the slices)
 //   mode 2  the slice of ONE owner rank, sequence number given by the host (staged exchange: one launch per owner
 //           block, so the mat-vec on the blocks that have arrived overlaps the transfer of the others)
-//   mode 3  the slices of all other ranks, host sequence number (staged exchange, operator not stored by owner block)
+//   mode 3  the slices of all other ranks, host sequence number (staged exchange, operator not stored by owner group)
+//   mode 4  the slices of the `count` ranks rank+owner, rank+owner+1, ... (mod P), this rank itself excepted (staged
+//           exchange, one launch per owner GROUP: the gathers on the groups that have arrived overlap the transfer
+//           of the others, and every pass gathers from an L2-sized part of x)
 struct XWait {
   PeerView pv;
   int mode = 0;
-  int owner = 0;
+  int owner = 0, count = 1;
   unsigned long long want = 0;
 };
 __device__ __forceinline__ void spmv_wait_x(const XWait &xw) {
@@ -95,8 +98,13 @@ __device__ __forceinline__ void spmv_wait_x(const XWait &xw) {
       peer_x_wait(xw.pv);
     else if (xw.mode == 2)
       peer_x_wait_one(xw.pv, xw.owner, xw.want);
-    else
+    else if (xw.mode == 3)
       peer_x_wait_others(xw.pv, xw.want);
+    else
+      for (int i = 0; i < xw.count; ++i) {
+        const int o = (xw.pv.rank + xw.owner + i) % xw.pv.P;
+        if (o != xw.pv.rank) peer_x_wait_one(xw.pv, o, xw.want);
+      }
   }
   __syncthreads();
 }
@@ -207,90 +215,6 @@ __global__ void __launch_bounds__(256)
       const int64_t r = rbase + (int64_t)u * ngroups;
       if (sub == 0 && r < n_rows) y[r] = accumulate ? Scalar<T>::add(y[r], s) : s;
     }
-  }
-}
-
-// ---- row-sharded mat-vec, all owner blocks in ONE launch -------------------------------------------------
-// The operator is stored block-major by OWNER rank of the column (b2a.cu build_owner_blocks).  A lane group owns
-// U rows for the whole launch and walks the owner blocks in arrival order of the staged exchange - its own block
-// first (gathered straight from the workspace column, no wait), then rank+1, rank+2, ... - keeping the U row sums in
-// registers: no read-modify-write of y between blocks, one launch instead of P, and the gathers on the blocks
-// that have arrived still hide the transfer of the others.  Before block k >= 1 the CTA waits for that owner's flag
-// (one polling thread + CTA barrier); the flags are written by copy engines, so CTAs that spin never block the
-// sender.  Every lane group reduces its rows in the same fixed order: deterministic.
-template <class T, int LPR, int U, int E>
-__global__ void __launch_bounds__(256)
-    spmv_owner_fused_kernel(int64_t n_rows, const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
-                            const T *__restrict__ vals, const T *__restrict__ x_own, const T *x_buf,
-                            T *__restrict__ y, const int *poison, const __grid_constant__ XWait xw) {
-  pdl_wait();
-  if (*poison) return;
-  const int P = xw.pv.P, me = xw.pv.rank;
-  const int sub = threadIdx.x & (LPR - 1);
-  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / LPR;  // host: ngroups * U >= n_rows
-  T acc[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) acc[u] = Scalar<T>::zero();
-  for (int k = 0; k < P; ++k) {
-    const int owner = (me + k) % P;
-    if (k > 0) {
-      if (threadIdx.x == 0) peer_x_wait_one(xw.pv, owner, xw.want);
-      __syncthreads();
-    }
-    const int64_t *rp = rowptr + (size_t)owner * (n_rows + 1);
-    int64_t rs[U], re[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t r = group + (int64_t)u * ngroups;
-      if (r < n_rows) {
-        rs[u] = __ldg(rp + r);
-        re[u] = __ldg(rp + r + 1);
-      } else {
-        rs[u] = re[u] = 0;
-      }
-    }
-    int32_t c[U][E];
-    T a[U][E];
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const int64_t i = rs[u] + sub + e * LPR;
-        const bool ok = i < re[u];
-        c[u][e] = ok ? __ldg(colind + i) : -1;
-        a[u][e] = ok ? ld_ro<T>(vals + i) : Scalar<T>::zero();
-      }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        T xv = Scalar<T>::zero();
-        if (c[u][e] >= 0) xv = k == 0 ? ld_ro<T>(x_own + c[u][e]) : ld_coh(x_buf + c[u][e]);
-        acc[u] = Scalar<T>::fma_(a[u][e], xv, acc[u]);
-      }
-    // (row, block) segments longer than E * LPR entries
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      for (int64_t i = rs[u] + sub + E * LPR; i < re[u]; i += LPR) {
-        const int32_t cc = __ldg(colind + i);
-        const T xv = k == 0 ? ld_ro<T>(x_own + cc) : ld_coh(x_buf + cc);
-        acc[u] = Scalar<T>::fma_(ld_ro<T>(vals + i), xv, acc[u]);
-      }
-  }
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    T s = acc[u];
-    if (Scalar<T>::is_complex) {
-      double2 *sp = reinterpret_cast<double2 *>(&s);
-      sp->x = group_sum_d<LPR>(sp->x);
-      sp->y = group_sum_d<LPR>(sp->y);
-    } else {
-      double *sp = reinterpret_cast<double *>(&s);
-      *sp = group_sum_d<LPR>(*sp);
-    }
-    const int64_t r = group + (int64_t)u * ngroups;
-    if (sub == 0 && r < n_rows) y[r] = s;
   }
 }
 

@@ -310,6 +310,11 @@ int b2a_host_sortschur(int dtype, void *H, int ldh, void *Q, int ldq, int maxdim
  * operator with n_global columns, `nnz_per_row` entries per row and a mean |column - row| of
  * `mean_col_distance` (in elements); 1 = plain CSR.  See the cost model at col_block_plan() in csrc/b2a.cu. */
 int b2a_host_col_block_plan(int dtype, int64_t n_global, double nnz_per_row, double mean_col_distance, int *nblocks);
+/* Owner groups of a row-sharded operator (host logic, no GPU): how many ranks' slices of x form one column block of
+ * the mat-vec (about 32 MB of x), how many blocks that gives, and - optionally - the block of every owner rank as
+ * seen from `rank` (block 0 = own slice and the ones that arrive first in the staged exchange). */
+int b2a_host_owner_group_plan(int dtype, int64_t n_global, int world, int rank, int *ranks_per_block, int *nblocks,
+                              int *block_of_owner);
 
 /* givensAlgorithm(f, g) -> (c, s, r); f, g, s, r are 1 (F64) or 2 (C64) doubles */
 int b2a_host_givens(int dtype, const double *f, const double *g, double *c, double *s, double *r);

@@ -94,6 +94,24 @@ function B200Operator(::Type{T}, n::Integer, f::Base.CFunction; ctx = default_co
     B200Operator{T}(r[], n, ctx)
 end
 
+# Shift-and-invert map x -> (A - sigma I) \ x on the device (the role of `construct_linear_map` in the reference's
+# docs/src/index.md:234-262, which wraps `factorize(A)` in a LinearMap): Jacobi-CG on the CSR mat-vec of `A`, for a
+# Hermitian positive definite A - sigma I.  `partialschur(shift_invert(Ad), which = :LM)`, then lambda = sigma + 1 / theta.
+function shift_invert(A::B200Operator{T}; sigma = zero(T), rtol = 1e-13, maxit = 10_000) where {T}
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:b2a_op_shift_invert, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Cint, Cdouble, Cint, Ref{Ptr{Cvoid}}),
+        A.ctx.h, A.h, real(sigma), imag(sigma), 0, rtol, maxit, r))
+    S = B200Operator{T}(r[], A.n, A.ctx)
+    finalizer(o -> (ccall((:b2a_op_destroy, LIB), Cint, (Ptr{Cvoid},), o.h); A), S)  # keeps A alive as long as S
+end
+
+function solve_stats(S::B200Operator)
+    solves, iters, worst = Ref{Int64}(0), Ref{Int64}(0), Ref{Cdouble}(0)
+    check(ccall((:b2a_op_solve_stats, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Cdouble}), S.h, solves, iters, worst))
+    (solves = solves[], iterations = iters[], worst_relres = worst[])
+end
+
 # ---- the device-resident basis: an AbstractMatrix whose storage is the library's workspace ----
 mutable struct B200Matrix{T} <: AbstractMatrix{T}
     ws::Ptr{Cvoid}          # b2a_ws*

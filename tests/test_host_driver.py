@@ -312,3 +312,33 @@ def test_column_block_plan_cost_model():
     assert _col_blocks(F64, 100_000_000, 64, 33_000_000) == 24
     # cfg 4 at full size (ComplexF64, x = 80 MB, 20 nnz/row): 3 blocks
     assert _col_blocks(C64, 5_000_000, 20, 1_600_000) == 3
+
+
+def test_owner_group_plan_of_row_sharded_operators():
+    """Row-sharded mat-vec: the column blocks are groups of owner ranks worth ~32 MB of x, numbered in the
+    order in which the staged exchange delivers the slices (own slice first, then rank+1, rank+2, ...)."""
+    import ctypes as C
+
+    from arnoldimethod_jl_b200 import _lib as L
+
+    def plan(dtype, n, world, rank):
+        g, nb = C.c_int(), C.c_int()
+        blk = (C.c_int * world)()
+        L.check(L.lib().b2a_host_owner_group_plan(dtype, n, world, rank, C.byref(g), C.byref(nb), blk))
+        return g.value, nb.value, list(blk)
+
+    F64, C64 = 0, 1
+    # bench.py at N = 2 / 4: x is 16 / 32 MB -> one block (no reordering; the mat-vec waits for the whole exchange)
+    assert plan(F64, 2_000_000, 2, 0)[:2] == (2, 1)
+    assert plan(F64, 4_000_000, 4, 1)[:2] == (4, 1)
+    # N = 8: 64 MB of x -> two blocks of four owners; rank 5 sees owners 5, 6, 7, 0 first, then 1, 2, 3, 4
+    g, nb, blk = plan(F64, 8_000_000, 8, 5)
+    assert (g, nb) == (4, 2) and blk == [0, 1, 1, 1, 1, 0, 0, 0]
+    # BASELINE cfg 5 (n = 1e8 on 8 GPUs): a slice alone is 100 MB -> one owner per block, own slice first
+    g, nb, blk = plan(F64, 100_000_000, 8, 2)
+    assert (g, nb) == (1, 8) and blk == [6, 7, 0, 1, 2, 3, 4, 5]
+    # BASELINE cfg 4 (ComplexF64 n = 5e6 on 2 GPUs): 40 MB slices -> one owner per block
+    assert plan(C64, 5_000_000, 2, 1) == (1, 2, [1, 0])
+    # ragged last block: 6 ranks, 12 MB slices -> groups of 2
+    g, nb, blk = plan(F64, 9_000_000, 6, 0)
+    assert (g, nb) == (2, 3) and blk == [0, 0, 1, 1, 2, 2]
