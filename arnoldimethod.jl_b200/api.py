@@ -181,7 +181,8 @@ class Operator:
                 colptr.dtype.itemsize * 8, int(idx_base), int(mode), C.byref(h),
             )
         )
-        return cls(ctx, h, dt, n_global, n_global, 0)
+        off, cnt = sharding.local_rows(int(n_global), ctx.rank, ctx.world)  # world == 1: the whole matrix
+        return cls(ctx, h, dt, cnt, n_global, off)
 
     @classmethod
     def from_matrix(cls, ctx, A, layout="auto", csc_mode=0):
@@ -194,8 +195,10 @@ class Operator:
             raise L.DimensionMismatch(f"matrix is not square: dimensions are {tuple(A.shape)}")
         n = A.shape[0]
         _, dt = _dtype_code(A.dtype)
-        if sp.issparse(A) and A.format == "csc" and layout in ("auto", "csc") and ctx.world == 1:
-            return cls.from_csc_arrays(ctx, A.indptr, A.indices, A.data.astype(dt, copy=False), n, 0, csc_mode)
+        if sp.issparse(A) and A.format == "csc" and layout in ("auto", "csc"):
+            # Julia's native layout as it is; row-sharded jobs keep this rank's row block (transpose at upload)
+            return cls.from_csc_arrays(ctx, A.indptr, A.indices, A.data.astype(dt, copy=False), n, 0,
+                                       csc_mode if ctx.world == 1 else 0)
         M = A.tocsr() if sp.issparse(A) else sp.csr_matrix(np.asarray(A))
         M.sort_indices()
         off, cnt, ip, idx, dat = sharding.shard_csr(M.indptr, M.indices, M.data, n, ctx.rank, ctx.world)

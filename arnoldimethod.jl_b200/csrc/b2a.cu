@@ -2324,7 +2324,10 @@ int b2a_csc_create(b2a_ctx *ctx, int dtype, int64_t n_global, int64_t nnz, const
   B2A_TRY(check_op_args(ctx, dtype, n_global, n_global, 0, nnz, idx_width, idx_base));
   if (!colptr || (nnz > 0 && (!rowval || !nzval)) || !out) return fail(B2A_ERR_ARGUMENT, "NULL array");
   ARG_CHECK(mode == 0 || mode == 1, "mode must be 0 (transpose at upload) or 1 (scatter kernel)");
-  if (ctx->world > 1) return fail(B2A_ERR_ARGUMENT, "CSC operators are single-GPU; shard rows as CSR");
+  // row-sharded job: every rank passes the WHOLE matrix in Julia's layout (as `A.colptr / A.rowval / A.nzval` would be
+  // on every process) and keeps the rows of its block of the uniform partition, transposed to CSR at upload
+  if (ctx->world > 1 && mode == 1)
+    return fail(B2A_ERR_ARGUMENT, "the CSC scatter kernel (mode 1) is single-GPU; row-sharded CSC operators use mode 0");
   if (mode == 1) {
     b2a_op *op = new b2a_op();
     op->ctx = ctx;
@@ -2349,9 +2352,13 @@ int b2a_csc_create(b2a_ctx *ctx, int dtype, int64_t n_global, int64_t nnz, const
     *out = op;
     return B2A_OK;
   }
-  // mode 0: one-time stable transpose to CSR on the host (setup, not the hot path), then upload
+  // mode 0: one-time stable transpose to CSR on the host (setup, not the hot path), then upload.  Only the rows of
+  // this rank's block [r0, r0 + nloc) of the uniform partition are kept (the whole matrix on a single GPU).
   const size_t es = dtype_size(dtype);
-  std::vector<int64_t> rowptr((size_t)n_global + 1, 0);
+  const int64_t W = cdiv(n_global, ctx->world);
+  const int64_t r0 = std::min<int64_t>((int64_t)ctx->rank * W, n_global);
+  const int64_t nloc = std::min<int64_t>(W, n_global - r0);
+  std::vector<int64_t> rowptr((size_t)nloc + 1, 0);
   auto ridx = [&](int64_t i) {
     return idx_width == 32 ? host_idx<int32_t>(rowval, i, idx_base) : host_idx<int64_t>(rowval, i, idx_base);
   };
@@ -2362,24 +2369,30 @@ int b2a_csc_create(b2a_ctx *ctx, int dtype, int64_t n_global, int64_t nnz, const
     return fail(B2A_ERR_ARGUMENT, "CSC: pointer array must start at 0 and end at nnz (check idx_base)");
   for (int64_t c = 0; c < n_global; ++c)
     if (cptr(c) > cptr(c + 1)) return fail(B2A_ERR_ARGUMENT, "CSC: pointer array must be non-decreasing");
+  int64_t nnz_loc = 0;
   for (int64_t i = 0; i < nnz; ++i) {
     const int64_t r = ridx(i);
     if (r < 0 || r >= n_global) return fail(B2A_ERR_ARGUMENT, "row index out of range in CSC input");
-    rowptr[(size_t)r + 1]++;
+    if (r >= r0 && r < r0 + nloc) {
+      rowptr[(size_t)(r - r0) + 1]++;
+      ++nnz_loc;
+    }
   }
-  for (int64_t r = 0; r < n_global; ++r) rowptr[(size_t)r + 1] += rowptr[(size_t)r];
+  for (int64_t r = 0; r < nloc; ++r) rowptr[(size_t)r + 1] += rowptr[(size_t)r];
   std::vector<int64_t> fill(rowptr.begin(), rowptr.end() - 1);
-  std::vector<int64_t> colind((size_t)nnz);
-  std::vector<char> vals((size_t)nnz * es);
+  std::vector<int64_t> colind((size_t)std::max<int64_t>(nnz_loc, 1));
+  std::vector<char> vals((size_t)std::max<int64_t>(nnz_loc, 1) * es);
   for (int64_t c = 0; c < n_global; ++c) {
     const int64_t s = cptr(c), e = cptr(c + 1);
     for (int64_t i = s; i < e; ++i) {
-      const int64_t dst = fill[(size_t)ridx(i)]++;
+      const int64_t r = ridx(i);
+      if (r < r0 || r >= r0 + nloc) continue;
+      const int64_t dst = fill[(size_t)(r - r0)]++;
       colind[(size_t)dst] = c;
       std::memcpy(&vals[(size_t)dst * es], reinterpret_cast<const char *>(nzval) + (size_t)i * es, es);
     }
   }
-  return b2a_csr_create(ctx, dtype, n_global, n_global, 0, nnz, rowptr.data(), colind.data(), vals.data(), 64, 0, out);
+  return b2a_csr_create(ctx, dtype, nloc, n_global, r0, nnz_loc, rowptr.data(), colind.data(), vals.data(), 64, 0, out);
 }
 
 int b2a_op_from_callback(b2a_ctx *ctx, int dtype, int64_t n_rows_local, int64_t n_global, b2a_matvec_fn matvec,

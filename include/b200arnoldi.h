@@ -125,10 +125,12 @@ int b2a_csr_create_device(b2a_ctx *ctx, int dtype, int64_t n_rows_local, int64_t
                           int64_t row_offset, int64_t nnz, const int64_t *d_rowptr,
                           const int32_t *d_colind, const void *d_vals, b2a_op **out);
 
-/* Julia's native SparseMatrixCSC: colptr (n_cols+1), rowval, nzval of the
- * n_global x n_global matrix (single-GPU) - `mode` selects the kernel:
- *   0 = transpose once on the device at upload, then the CSR kernel (deterministic);
- *   1 = native column-scatter kernel (red.global.add.f64; sums in arrival order). */
+/* Julia's native SparseMatrixCSC: colptr (n_cols+1), rowval, nzval of the WHOLE
+ * n_global x n_global matrix - `mode` selects the kernel:
+ *   0 = transpose once at upload, then the CSR kernel (deterministic).  In a row-sharded job every rank passes
+ *       the whole matrix (as every Julia process would hold `A.colptr / A.rowval / A.nzval`) and keeps the rows
+ *       of its block of the uniform partition (ceil(n / world) rows per rank);
+ *   1 = native column-scatter kernel (red.global.add.f64; sums in arrival order; single GPU only). */
 int b2a_csc_create(b2a_ctx *ctx, int dtype, int64_t n_global, int64_t nnz, const void *colptr,
                    const void *rowval, const void *nzval, int idx_width, int idx_base, int mode,
                    b2a_op **out);

@@ -188,6 +188,13 @@ def main():
             print(f"{T.__name__}: world={world} mvproducts={hist.mvproducts} (oracle {ho.mvproducts}) "
                   f"H err={err:.1e} ||AQ-QR||={res:.2e} collectives={P.workspace.comm_mode} "
                   f"fused_sweep={os.environ.get('B2A_FUSED_SWEEP', 'default')}", flush=True)
+        # Julia's native CSC layout, row-sharded: every rank passes the whole matrix and keeps its row block
+        # (b2a_csc_create mode 0 transposes at upload) - same rows, same order, hence the very same run
+        P.workspace.close()
+        Pc, hc = b2a.partialschur(A.tocsc(), nev=nev, tol=1e-8, which="LM", v1=v1, ctx=ctx)
+        assert hc.mvproducts == hist.mvproducts and hc.nconverged == hist.nconverged
+        assert np.array_equal(Pc.eigenvalues, P.eigenvalues) and np.array_equal(Pc.R, P.R)
+        Pc.workspace.close()
         # the result keeps its workspace (Q is a view of V): release it so that the next workspace of this
         # context gets the NVLink peer block again (one owner at a time; others fall back to NCCL)
         P.workspace.close()
