@@ -155,6 +155,7 @@ struct b2a_ctx {
   // publications, and the exchange counter every rank advances in lockstep (see enqueue_matvec)
   std::vector<cudaStream_t> xchg_streams;
   std::vector<cudaEvent_t> xchg_done;   // one per side stream: its last transfer + publication
+  cudaEvent_t xchg_data_ev[2] = {nullptr, nullptr};  // chained exchange: data transfer of the previous stage done
   cudaEvent_t xchg_ready = nullptr;     // main stream: the column to exchange is final
   unsigned long long x_seq = 0;
   // device table of consecutive exchange numbers: the per-slice flag is published by an 8-byte COPY-ENGINE transfer
@@ -923,15 +924,25 @@ static int xchg_ensure_table(b2a_ctx *ctx, unsigned long long seq) {
   return B2A_OK;
 }
 
-static int g_xchg_nstreams = getenv("B2A_XCHG_STREAMS") ? std::max(1, atoi(getenv("B2A_XCHG_STREAMS"))) : 3;
+// Side streams of the staged exchange.  Measured at N = 8 (profiles/r2_variants_n8_streams.txt): the outgoing 56 MB
+// take 145-180 us whatever the stream count (copy-engine rate), but with ONE stream the stages arrive in the order
+// the mat-vec consumes them - 224 us per mat-vec and 36.2 ms per solve against 255 us / 40.1 ms with three streams
+// (concurrent stages all arrive late) and 271 us / 41.9 ms with seven.
+static int g_xchg_nstreams = getenv("B2A_XCHG_STREAMS") ? std::max(1, atoi(getenv("B2A_XCHG_STREAMS"))) : 1;
+// B2A_XCHG_CHAIN=1 (experiment): two streams, the data transfer of stage k+1 starts right behind the data transfer of
+// stage k (event), so the flag transfers and launch latencies leave the critical path while the stages stay ordered
+static bool g_xchg_chain = getenv("B2A_XCHG_CHAIN") && getenv("B2A_XCHG_CHAIN")[0] == '1';
 
 // Enqueue the exchange of workspace column jsrc0; returns the exchange number the consumers wait for.
 template <class DT> static int enqueue_xchg(b2a_ws *ws, const DT *xl, unsigned long long *seq_out) {
   b2a_ctx *ctx = ws->ctx;
   const b2a::PeerView &pv = ws->peer;
   const int P = pv.P, me = pv.rank;
-  const int ns = std::min(g_xchg_nstreams, P - 1);
+  const bool chain = g_xchg_chain && P > 2;
+  const int ns = chain ? 2 : std::min(g_xchg_nstreams, P - 1);
   B2A_TRY(xchg_ensure_streams(ctx, ns));
+  if (chain && !ctx->xchg_data_ev[0])
+    for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreateWithFlags(&ctx->xchg_data_ev[i], cudaEventDisableTiming));
   const unsigned long long seq = ++ctx->x_seq;
   B2A_TRY(xchg_ensure_table(ctx, seq));
   const unsigned long long *seq_src = ctx->xchg_seq_table + (seq - ctx->xchg_table_base);
@@ -939,24 +950,29 @@ template <class DT> static int enqueue_xchg(b2a_ws *ws, const DT *xl, unsigned l
   const size_t xoff = pv.off_x + (seq & 1ull) * pv.x_stride + (size_t)ws->row_offset * sizeof(DT);
   CUDA_TRY(cudaEventRecord(ctx->xchg_ready, ctx->stream));
   for (int i = 0; i < ns; ++i) CUDA_TRY(cudaStreamWaitEvent(ctx->xchg_streams[i], ctx->xchg_ready, 0));
-  // timed on the first side stream: with ns streams it carries ceil((P-1)/ns) of the P-1 stages
-  const int on_first = (P - 1 + ns - 1) / ns;
-  prof_begin(ctx, B2A_K_XCHG, (double)bytes * on_first, 0, ctx->xchg_streams[0]);
+  // timed from "column final" to "every outgoing stage done": bytes = what this rank sends
+  prof_begin(ctx, B2A_K_XCHG, (double)bytes * (P - 1), 0, ctx->xchg_streams[0]);
   for (int k = 1; k < P; ++k) {
     const int dst = (me - k + P) % P;
     cudaStream_t st = ctx->xchg_streams[(k - 1) % ns];
     unsigned long long *flag = reinterpret_cast<unsigned long long *>(pv.peer[dst] + pv.off_flag_xs) + me;
     // slice, then its flag: both copy-engine transfers, ordered by the stream
+    if (chain && k > 1) CUDA_TRY(cudaStreamWaitEvent(st, ctx->xchg_data_ev[(k - 2) & 1], 0));
     if (bytes) CUDA_TRY(cudaMemcpyAsync(pv.peer[dst] + xoff, xl, bytes, cudaMemcpyDeviceToDevice, st));
+    if (chain) CUDA_TRY(cudaEventRecord(ctx->xchg_data_ev[(k - 1) & 1], st));
     CUDA_TRY(cudaMemcpyAsync(flag, seq_src, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
   }
   for (int i = 0; i < ns; ++i) CUDA_TRY(cudaEventRecord(ctx->xchg_done[i], ctx->xchg_streams[i]));
-  if (ctx->prof_on) {  // e1 of the exchange record: after the last operation of the first side stream
+  if (ctx->prof_on) {
+    // e1 of the exchange record: when ALL side streams have finished their stages (the first stream waits for the
+    // others - it has nothing else to do), so the record is the duration of this rank's whole outgoing exchange
+    for (int i = 1; i < ns; ++i) CUDA_TRY(cudaStreamWaitEvent(ctx->xchg_streams[0], ctx->xchg_done[i], 0));
     for (auto it = ctx->prof_pending.rbegin(); it != ctx->prof_pending.rend(); ++it)
       if (it->kind == B2A_K_XCHG) {
         cudaEventRecord(it->e1, ctx->xchg_streams[0]);
         break;
       }
+    CUDA_TRY(cudaEventRecord(ctx->xchg_done[0], ctx->xchg_streams[0]));
   }
   *seq_out = seq;
   return B2A_OK;
@@ -1057,7 +1073,7 @@ template <class DT> static int enqueue_matvec(b2a_ws *ws, b2a_op *A, int jsrc0, 
   if (ctx->world > 1 && ws->peer.P > 1 && ws->xchg_staged) {
     unsigned long long seq = 0;
     B2A_TRY(enqueue_xchg<DT>(ws, xl, &seq));
-    xchg_streams_used = std::min(g_xchg_nstreams, ws->peer.P - 1);
+    xchg_streams_used = (g_xchg_chain && ws->peer.P > 2) ? 2 : std::min(g_xchg_nstreams, ws->peer.P - 1);
     const DT *xbuf = reinterpret_cast<const DT *>(ws->peer.peer[ws->peer.rank] + ws->peer.off_x + (seq & 1ull) * ws->peer.x_stride);
     xw.pv = ws->peer;
     xw.want = seq;
@@ -1767,6 +1783,8 @@ int b2a_ctx_destroy(b2a_ctx *ctx) {
   for (auto e : ctx->xchg_done) cudaEventDestroy(e);
   if (ctx->xchg_ready) cudaEventDestroy(ctx->xchg_ready);
   if (ctx->xchg_seq_table) cudaFree(ctx->xchg_seq_table);
+  for (int i = 0; i < 2; ++i)
+    if (ctx->xchg_data_ev[i]) cudaEventDestroy(ctx->xchg_data_ev[i]);
   if (ctx->comm) g_nccl.CommDestroy(ctx->comm);
   if (ctx->d_zero) cudaFree(ctx->d_zero);
   for (auto &pc : ctx->pinned_cache) cudaFreeHost(pc.second);

@@ -99,8 +99,8 @@ enum b2a_kernel_kind {
   B2A_K_FILL = 5,   /* counter-based rand!                                               */
   B2A_K_SWEEP = 6,  /* fused orthogonalisation (dots + update [+ update] + finish in one
                        persistent kernel)     bytes/launch = (2j+5) n s [+ (j+2) n s]   */
-  B2A_K_XCHG = 7,   /* staged x exchange of a row-sharded mat-vec, timed on its first side stream:
-                       bytes/launch = NVLink bytes this rank SENDS, (P-1) n_loc s (never added to HBM) */
+  B2A_K_XCHG = 7,   /* staged x exchange of a row-sharded mat-vec, from "column final" to "all outgoing
+                       stages done": bytes/launch = NVLink bytes this rank SENDS, (P-1) n_loc s          */
   B2A_K_COUNT = 8
 };
 int b2a_ctx_profile_enable(b2a_ctx *ctx, int on); /* also resets the accumulators */
