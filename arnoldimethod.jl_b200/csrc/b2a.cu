@@ -1007,14 +1007,30 @@ template <class DT> static int spmv_plain(b2a_ctx *ctx, b2a_op *A, const DT *x, 
 
 // y = (A - sigma I)^{-1} b by Jacobi-preconditioned CG (kernels_solve.cuh).  Iterations are enqueued in chunks; the
 // device raises `done` itself, the host looks once per chunk.
+template <class DT> static inline DT host_scalar(double re, double im);
+template <> inline double host_scalar<double>(double re, double) { return re; }
+template <> inline cdouble host_scalar<cdouble>(double re, double im) { return make_double2(re, im); }
+
+static const bool g_trace = getenv("B2A_TRACE") != nullptr;
+#define B2A_TRACE(...)                 \
+  do {                                 \
+    if (g_trace) {                     \
+      fprintf(stderr, "[b2a] " __VA_ARGS__); \
+      fputc('\n', stderr);             \
+      fflush(stderr);                  \
+    }                                  \
+  } while (0)
+
 template <class DT> static int enqueue_shift_invert(b2a_ws *ws, b2a_op *S, const DT *b, DT *y) {
   b2a_ctx *ctx = ws->ctx;
+  B2A_TRACE("shift-invert solve: n=%lld inner=%p work=%p cg=%p host=%p", (long long)S->n_local, (void *)S->inner,
+            S->solve_work, (void *)S->cg, (void *)S->cg_host);
   b2a_op *A = S->inner;
   const int64_t n = S->n_local;
   const int *poison = &ws->state->poison;
   DT *d = reinterpret_cast<DT *>(S->solve_work);
   DT *r = d + n, *z = r + n, *p = z + n, *q = p + n;
-  const DT sigma = b2a::make_scalar<DT>(S->sigma_re, S->sigma_im);
+  const DT sigma = host_scalar<DT>(S->sigma_re, S->sigma_im);  // (the device helper make_scalar must not be called here)
   const int has_sigma = (S->sigma_re != 0.0 || S->sigma_im != 0.0) ? 1 : 0;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->num_sms * 4, cdiv(n, b2a::kSolveThreads)));
   prof_begin(ctx, B2A_K_SPMV, 0.0);
@@ -1039,6 +1055,8 @@ template <class DT> static int enqueue_shift_invert(b2a_ws *ws, b2a_op *S, const
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(S->cg_host, S->cg, sizeof(b2a::CgState), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    B2A_TRACE("  chunk done: it=%d done=%d iters=%d rr=%g bb=%g", it, S->cg_host->done, S->cg_host->iters, S->cg_host->rr,
+              S->cg_host->bb);
     finished = S->cg_host->done != 0 || it >= S->solve_maxit;
   }
   prof_end(ctx);
