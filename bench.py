@@ -89,9 +89,10 @@ def ncu_traffic_table():
 
 
 LIMITER_NOTES = {
-    "spmv": "uniformly random columns: every 8-byte gather of x moves a 32-byte sector through L2->L1; ncu: "
-            "lts__throughput 70 %, l1tex__throughput 72 % of peak, DRAM traffic == algorithmic bytes. "
-            "HBM-bound only on structured matrices (7-pt stencil: 4.85 TB/s = 74 % of peak).",
+    "spmv": "uniformly random columns: every 8-byte gather of x is its own 32-byte sector; ncu "
+            "(profiles/r2_ncu_spmv_summary.txt): 24.6 M L1TEX sectors / 148 SMs / 169 K cycles = 0.98 per SM-cycle - the "
+            "L1TEX tag stage (1 sector/clk) is saturated; L2 at 69 %, DRAM traffic == algorithmic bytes (30 %). "
+            "HBM-bound only on structured matrices (7-pt stencil: 5.15 TB/s = 79 % of peak).",
     "cgs_sweep": "HBM stream of the Krylov panel through a TMA ring, 2-3 passes per launch (dots, update + "
                  "speculative dots, gated second update, normalisation fused in one persistent kernel); the passes "
                  "run at 6.0-6.5 TB/s, the rest is 2-3 in-kernel grid barriers (~4 us each) and the launch",
@@ -375,6 +376,11 @@ def run_gpu(args):
                                           f"{tt['dram_over_algorithmic']} ({tt['source']}) x the algorithmic bytes "
                                           f"per launch measured in this run")
         roofline["limiter"] = LIMITER_NOTES.get(top)
+        if world > 1 and top == "spmv":
+            roofline["limiter"] = (
+                "row-sharded mat-vec: the launch(es) wait for the slices of x they gather from (staged copy-engine "
+                "exchange over NVLink, 'xchg' in roofline.kernels = its true duration on this rank), so the time "
+                "includes that wait; the gathers themselves run at the L1TEX sector rate as on one GPU. " + LIMITER_NOTES["spmv"])
         # context: the HBM-streaming Gram-Schmidt sweeps (dots + update) taken together, and all kernels
         gs = [prof[k] for k in ("cgs_dots", "cgs_update", "cgs_sweep") if k in prof and prof[k]["launches"]]
         if gs:

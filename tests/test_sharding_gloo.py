@@ -139,3 +139,54 @@ def test_sharded_arnoldi_matches_unsharded_oracle(tmp_path):
     assert np.abs(H0 - arn.H).max() < 1e-12 * np.abs(arn.H).max()
     V = np.vstack([np.load(tmp_path / "V0.npy"), np.load(tmp_path / "V1.npy")])
     assert np.abs(V - arn.V).max() < 1e-10
+
+
+def _owner_plan(dtype_code, n, world, rank):
+    import ctypes as C
+
+    from arnoldimethod_jl_b200 import _lib as L
+
+    g, nb = C.c_int(), C.c_int()
+    blk = (C.c_int * world)()
+    L.check(L.lib().b2a_host_owner_group_plan(dtype_code, int(n), int(world), int(rank), C.byref(g), C.byref(nb), blk))
+    return g.value, nb.value, list(blk)
+
+
+@pytest.mark.parametrize("world,n", [(2, 2_000_000), (3, 9_000_000), (4, 4_000_000), (6, 9_000_000), (8, 8_000_000),
+                                     (8, 100_000_000), (5, 50_000_000)])
+def test_staged_exchange_schedule_matches_owner_groups(world, n):
+    """The staged x exchange and the owner-group mat-vec agree, for the library's own plan
+    (`b2a_host_owner_group_plan`, the function `b2a_csr_create` uses):
+      * stage k = 1 .. P-1 sends the slice of rank s to rank (s - k) mod P: every stage is a permutation, so each
+        NVLink port carries one slice in and one out, and after P - 1 stages every rank holds every slice;
+      * rank r therefore receives owners r+1, r+2, ... in that order, and the column blocks of its operator are numbered
+        in exactly that order (block 0 = own slice first): a pass never waits for a slice that arrives after a slice of
+        a later block;
+      * the blocked mat-vec (one pass per block, accumulating) reproduces the plain one."""
+    P = world
+    have = [{r} for r in range(P)]
+    for k in range(1, P):
+        receivers = [(s - k) % P for s in range(P)]
+        assert sorted(receivers) == list(range(P))  # a permutation per stage
+        for s, r in enumerate(receivers):
+            have[r].add(s)
+    assert all(h == set(range(P)) for h in have)
+    for r in range(P):
+        G, nb, blk = _owner_plan(0, n, P, r)
+        assert nb == -(-P // G) and blk[r] == 0
+        arrival = [r] + [(r + k) % P for k in range(1, P)]
+        order = [blk[o] for o in arrival]
+        assert order == sorted(order)  # blocks are consumed in arrival order
+        assert all(order.count(b) == min(G, P - b * G) for b in range(nb))
+    # numerics of the blocked mat-vec on a small shard with this very block map
+    rng = np.random.default_rng(world)
+    m = 40 * P
+    W = -(-m // P)
+    A = sp.random(W, m, 0.2, random_state=rng, format="csr")
+    x = rng.standard_normal(m)
+    G, nb, blk = _owner_plan(0, n, P, 1 % P)
+    y = np.zeros(W)
+    for b in range(nb):
+        cols = np.array([blk[min(c // W, P - 1)] == b for c in range(m)])
+        y += A[:, cols] @ x[cols]
+    assert np.allclose(y, A @ x, rtol=1e-13, atol=1e-13)
