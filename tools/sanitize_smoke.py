@@ -32,5 +32,13 @@ for T in (np.float64, np.complex128):
     ws.reinitialize(0, "keep")
     ws.iterate_arnoldi(op, 1, 70)
     ws.norm(3), ws.gemv_c(5, 6), ws.scal_div(71, 2.0), ws.copy_col(1, 2)
-    print(T.__name__, "ok", hist)
+    ws.rotate_basis(3, 41, 70, np.asfortranarray(np.linalg.qr(rng.standard_normal((70, 70)))[0].astype(T)))  # DMMA, N > 32
+    # shift-and-invert (Jacobi-CG kernels) on a Hermitian positive definite operator
+    B = sp.random(n, n, 3 / n, random_state=rng, format="csr").astype(T)
+    S_ = (B.conj().T @ B + sp.identity(n) * 2.0).tocsr().astype(T)
+    S_.sort_indices()
+    ops = b2a.Operator.from_matrix(ctx, S_)
+    inv = b2a.Operator.shift_invert(ops, sigma=0.5)
+    ws.matvec(inv, 1, 2)
+    print(T.__name__, "ok", hist, inv.solve_stats)
 print("SANITIZE_SMOKE_DONE")
