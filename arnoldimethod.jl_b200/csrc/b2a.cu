@@ -333,7 +333,7 @@ struct b2a_ws {
   int x_pushed_col = -1;  // 0-based column whose normalised content currently sits in every rank's x buffer
   // staged exchange (default on row-sharded workspaces that own the peer block; B2A_XCHG=0 selects the push from
   // inside the normalising kernel): copy-engine transfers on side streams, one flag per owner slice, the mat-vec
-  // runs owner block by owner block behind the arrivals.
+  // runs owner group by owner group behind the arrivals.
   bool xchg_staged = false;
   // rotation: Q travels host -> device through two alternating pinned slots (no stream synchronisation per
   // rotation: a slot is re-used only after the event behind its last copy)
@@ -891,7 +891,7 @@ template <class DT> static int launch_spmv_tma(b2a_op *A, const DT *x, DT *y, co
 // copy-engine transfer that publishes the exchange number in the receiver's flag for this sender (stream order
 // puts it behind the data).  No kernel is involved on the sending side: the mat-vec launches that spin on the
 // flags can occupy every SM slot of a GPU, and a flag-publishing kernel queued behind them would never start
-// while its peer waits for that very flag.  The receiver runs its mat-vec owner block by owner block in the same order
+// while its peer waits for that very flag.  The receiver runs its mat-vec owner group by owner group in the same order
 // (own block, rank+1, rank+2, ...): the gathers on the blocks that have arrived hide the transfer of the others.
 // Two x buffers (exchange-number parity): a rank that is one mat-vec ahead never overwrites what a peer still reads.
 static int xchg_ensure_streams(b2a_ctx *ctx, int want) {

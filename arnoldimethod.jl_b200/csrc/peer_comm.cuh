@@ -192,7 +192,7 @@ __device__ __forceinline__ void peer_x_wait_one(const PeerView &pv, int owner, u
     }
   }
 }
-// ... or for the slices of all other ranks (operators that are not stored by owner block)
+// ... or for the slices of all other ranks (operators that are not stored by owner group)
 __device__ __forceinline__ void peer_x_wait_others(const PeerView &pv, unsigned long long want) {
   for (int p = 0; p < pv.P; ++p)
     if (p != pv.rank) peer_x_wait_one(pv, p, want);
